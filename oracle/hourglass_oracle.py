@@ -22,8 +22,14 @@ import torch.nn.functional as F
 BN_EPS = 1e-5  # torch.nn.BatchNorm2d default used everywhere in the reference
 
 
+_CALIBRATE = [False]
+
+
 def _bn(sd: Dict[str, torch.Tensor], p: str, x: torch.Tensor) -> torch.Tensor:
     """Eval-mode BatchNorm2d with running statistics."""
+    if _CALIBRATE[0]:   # see calibrate_bn(): overwrite running stats with this batch's statistics
+        sd[p + ".running_mean"] = x.mean(dim=(0, 2, 3))
+        sd[p + ".running_var"] = x.var(dim=(0, 2, 3), unbiased=False)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"],
                         sd[p + ".weight"], sd[p + ".bias"], False, 0.0, BN_EPS)
 
@@ -114,11 +120,11 @@ def hg_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor,
 # Deterministic synthetic weights with the reference's state_dict layout.
 # ---------------------------------------------------------------------------
 
-def _conv_init(g, cout, cin_per_group, k, gain=1.0):
-    """Kaiming-uniform-like init (what nn.Conv2d does by default), seeded."""
-    fan_in = cin_per_group * k * k
-    bound = gain / math.sqrt(fan_in)
-    w = (torch.rand(cout, cin_per_group, k, k, generator=g) * 2 - 1) * bound * math.sqrt(3.0)
+def _conv_init(g, cout, cin_per_group, k):
+    """nn.Conv2d's default init (kaiming_uniform_(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+    for both weight and bias), seeded -- SURVEY.md section 8d "default init"."""
+    bound = 1.0 / math.sqrt(cin_per_group * k * k)
+    w = (torch.rand(cout, cin_per_group, k, k, generator=g) * 2 - 1) * bound
     b = (torch.rand(cout, generator=g) * 2 - 1) * bound
     return w, b
 
@@ -190,6 +196,22 @@ def make_state_dict(num_stacks=2, num_blocks=1, num_classes=16, mobile=False,
         if i < num_stacks - 1:
             conv(f"fc_.{i}", ch, ch, 1)
             conv(f"score_.{i}", num_classes, ch, 1)
+    return sd
+
+
+def calibrate_bn(sd, x: torch.Tensor):
+    """Replace every BN's running statistics by the batch statistics seen on `x`.
+
+    Random conv weights with arbitrary running stats make activations grow ~10x per
+    stack; calibrating gives a well-conditioned network (unit-variance pre-activations,
+    like a trained one) whose weights are still fully synthetic and seeded.  In place.
+    """
+    _CALIBRATE[0] = True
+    try:
+        with torch.no_grad():
+            hg_forward(sd, x)
+    finally:
+        _CALIBRATE[0] = False
     return sd
 
 
