@@ -1,0 +1,266 @@
+"""Tensor-level wrappers over the C ABI.  torch supplies memory and the current stream only."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ._lib import lib, ConvDesc, HgError
+
+_err_words = {}
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise HgError("hgb200 ops run on CUDA tensors only (no CPU fallback)")
+        if not t.is_contiguous():
+            raise HgError("hgb200 ops need contiguous tensors")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def err_word(device=None) -> torch.Tensor:
+    """Per-device uint32 word that kernels set when a bounded mbarrier wait times out."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    w = _err_words.get(key)
+    if w is None:
+        w = torch.zeros(1, dtype=torch.int32, device=dev)
+        _err_words[key] = w
+    return w
+
+
+def check_err_word(device=None):
+    """Synchronises and raises if any kernel reported a protocol timeout."""
+    w = err_word(device)
+    v = int(w.item())
+    if v != 0:
+        w.zero_()
+        raise HgError(f"device-side protocol timeout, code 0x{v & 0xffffffff:x} (role<<8 | barrier)")
+
+
+def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksize: int, cout: int,
+              relu: bool = False, in_scale: Optional[torch.Tensor] = None, in_shift: Optional[torch.Tensor] = None,
+              residual: Optional[torch.Tensor] = None, up_low: Optional[torch.Tensor] = None,
+              x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              out_nchw_f32: Optional[torch.Tensor] = None, heads: bool = False) -> torch.Tensor:
+    """Implicit-GEMM conv on tcgen05 (hg_conv_nhwc_bf16).
+
+    x: bf16 [n,h,w,cin]; weight: bf16 [cout_pad, taps*cin (+cin2)]; bias fp32 [cout_pad].
+    heads=True -> returns fp32 NCHW [n,cout,h,w]; else bf16 NHWC [n,h,w,cout].
+    """
+    _require_cuda(x, weight, bias, in_scale, in_shift, residual, up_low, x2, out, out_nchw_f32)
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or bias.dtype != torch.float32:
+        raise HgError("conv_nhwc: x/weight must be bf16 and bias fp32")
+    n, h, w, cin = x.shape
+    cin2 = 0 if x2 is None else x2.shape[-1]
+    cout_pad = (cout + 15) // 16 * 16
+    ktot = ksize * ksize * cin + cin2
+    if tuple(weight.shape) != (cout_pad, ktot) or bias.numel() != cout_pad:
+        raise HgError(f"conv_nhwc: weight {tuple(weight.shape)} / bias {bias.numel()} do not match "
+                      f"[{cout_pad},{ktot}]")
+    d = ConvDesc()
+    if heads:
+        if out_nchw_f32 is None:
+            out_nchw_f32 = torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device)
+        result = out_nchw_f32
+    else:
+        if out is None:
+            out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x.device)
+        result = out
+    for t, shape in ((residual, (n, h, w, cout)), (up_low, (n, h // 2, w // 2, cout)), (x2, (n, h, w, cin2))):
+        if t is not None and (tuple(t.shape) != shape or t.dtype != torch.bfloat16):
+            raise HgError(f"conv_nhwc: operand shape {tuple(t.shape)} != {shape} or not bf16")
+    d.in_, d.in2, d.weight, d.bias = x.data_ptr(), (x2.data_ptr() if x2 is not None else None), weight.data_ptr(), bias.data_ptr()
+    d.in_scale = in_scale.data_ptr() if in_scale is not None else None
+    d.in_shift = in_shift.data_ptr() if in_shift is not None else None
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.up_low = up_low.data_ptr() if up_low is not None else None
+    d.out = None if heads else out.data_ptr()
+    d.out_nchw_f32 = out_nchw_f32.data_ptr() if heads else None
+    d.err_word = err_word(x.device).data_ptr()
+    d.n, d.h, d.w, d.cin, d.cin2, d.cout, d.ksize, d.relu = n, h, w, cin, cin2, cout, ksize, int(relu)
+    lib.check(lib.hg_conv_nhwc_bf16(C.byref(d), _stream()), "hg_conv_nhwc_bf16")
+    return result
+
+
+def stem_im2col(x_nchw: torch.Tensor, flip_w: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 NCHW [n,3,h,w] -> bf16 [n, h/2, w/2, 192] im2col rows of the 7x7/s2 stem conv."""
+    _require_cuda(x_nchw, out)
+    n, c, h, w = x_nchw.shape
+    if c != 3 or x_nchw.dtype != torch.float32:
+        raise HgError("stem_im2col: expects fp32 [n,3,h,w]")
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, 192), dtype=torch.bfloat16, device=x_nchw.device)
+    lib.check(lib.hg_stem_im2col(_ptr(x_nchw), _ptr(out), n, h, w, int(flip_w), _stream()), "hg_stem_im2col")
+    return out
+
+
+def maxpool2x2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x, out)
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+    lib.check(lib.hg_maxpool2x2_nhwc(_ptr(x), _ptr(out), n, h, w, c, _stream()), "hg_maxpool2x2_nhwc")
+    return out
+
+
+def upsample2x_add(a: torch.Tensor, low: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(a, low, out)
+    n, h, w, c = a.shape
+    if out is None:
+        out = torch.empty_like(a)
+    lib.check(lib.hg_upsample2x_add_nhwc(_ptr(a), _ptr(low), _ptr(out), n, h, w, c, _stream()), "hg_upsample2x_add_nhwc")
+    return out
+
+
+def bn_relu(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x, scale, shift, out)
+    c = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    lib.check(lib.hg_bn_relu_nhwc(_ptr(x), _ptr(scale), _ptr(shift), _ptr(out), x.numel() // c, c, _stream()),
+              "hg_bn_relu_nhwc")
+    return out
+
+
+def nchw_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x)
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=x.device)
+    lib.check(lib.hg_nchw_f32_to_nhwc_bf16(_ptr(x.float()), _ptr(out), n, c, h, w, _stream()), "hg_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_bf16_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    lib.check(lib.hg_nhwc_bf16_to_nchw_f32(_ptr(x), _ptr(out), n, c, h, w, _stream()), "hg_nhwc_bf16_to_nchw_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ decode
+def _hm(hm: torch.Tensor) -> torch.Tensor:
+    if hm.dim() != 4:
+        raise AssertionError("Score maps should be 4-dim")       # same message as evaluation.py:13
+    if not hm.is_cuda:
+        if not torch.cuda.is_available():
+            raise HgError("hgb200 decode needs a CUDA device (no CPU fallback)")
+        hm = hm.cuda()
+    return hm.detach().float().contiguous()
+
+
+def decode_argmax(hm: torch.Tensor):
+    """-> (preds fp32 [b,j,2], maxval fp32 [b,j], idx int32 [b,j]) on the heat map's device."""
+    hm = _hm(hm)
+    b, j, h, w = hm.shape
+    preds = torch.empty((b, j, 2), dtype=torch.float32, device=hm.device)
+    maxval = torch.empty((b, j), dtype=torch.float32, device=hm.device)
+    idx = torch.empty((b, j), dtype=torch.int32, device=hm.device)
+    lib.check(lib.hg_decode_argmax(_ptr(hm), _ptr(preds), _ptr(maxval), _ptr(idx), b, j, h, w, _stream()),
+              "hg_decode_argmax")
+    return preds, maxval, idx
+
+
+def decode_final_preds(hm: torch.Tensor, center, scale, output_size) -> torch.Tensor:
+    """Batched get_final_preds_v1: center/scale [b,2] (array-like), -> fp64 [b,j,2] on device."""
+    hm = _hm(hm)
+    b, j, h, w = hm.shape
+    c = torch.as_tensor(np.asarray(center, dtype=np.float64).reshape(b, 2)).to(hm.device)
+    s = torch.as_tensor(np.asarray(scale, dtype=np.float64).reshape(b, 2)).to(hm.device)
+    out = torch.empty((b, j, 2), dtype=torch.float64, device=hm.device)
+    lib.check(lib.hg_decode_final_preds(_ptr(hm), _ptr(c), _ptr(s), _ptr(out), b, j, h, w, int(output_size[0]),
+                                        int(output_size[1]), _stream()), "hg_decode_final_preds")
+    return out
+
+
+def flip_average(hm: torch.Tensor, hm_flip: torch.Tensor, perm: torch.Tensor, out: Optional[torch.Tensor] = None):
+    hm, hm_flip = _hm(hm), _hm(hm_flip)
+    _require_cuda(perm)
+    b, j, h, w = hm.shape
+    if out is None:
+        out = torch.empty_like(hm)
+    lib.check(lib.hg_flip_average(_ptr(hm), _ptr(hm_flip), _ptr(perm), _ptr(out), b, j, h, w, _stream()), "hg_flip_average")
+    return out
+
+
+def pck_dists(out_hm: torch.Tensor, tgt_hm: torch.Tensor) -> torch.Tensor:
+    out_hm, tgt_hm = _hm(out_hm), _hm(tgt_hm)
+    b, j, h, w = out_hm.shape
+    d = torch.empty((j, b), dtype=torch.float32, device=out_hm.device)
+    lib.check(lib.hg_pck_dists(_ptr(out_hm), _ptr(tgt_hm), _ptr(d), b, j, h, w, _stream()), "hg_pck_dists")
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ loss / targets
+_patch_cache = {}
+
+
+def gaussian_patch(sigma, device) -> torch.Tensor:
+    """The reference's un-normalised Gaussian patch (common.py:229-236), computed with numpy in float32
+    exactly as the reference does, so on-device targets are bit-identical to generate_target's."""
+    key = (float(sigma), str(device))
+    p = _patch_cache.get(key)
+    if p is None:
+        tmp = sigma * 3
+        size = 2 * tmp + 1
+        x = np.arange(0, size, 1, np.float32)
+        y = x[:, np.newaxis]
+        x0 = y0 = size // 2
+        g = np.exp(-((x - x0) ** 2 + (y - y0) ** 2) / (2 * sigma ** 2))
+        p = torch.from_numpy(np.ascontiguousarray(g, dtype=np.float32)).to(device)
+        _patch_cache[key] = p
+    return p
+
+
+def joint_centers(joints: torch.Tensor, vis: torch.Tensor, heatmap_size, image_size, sigma=1):
+    """joints/vis fp64 [b,j,3] (device) -> (mu int32 [b,j,2], weight fp32 [b,j])."""
+    _require_cuda(joints, vis)
+    b, j = joints.shape[:2]
+    mu = torch.empty((b, j, 2), dtype=torch.int32, device=joints.device)
+    wt = torch.empty((b, j), dtype=torch.float32, device=joints.device)
+    lib.check(lib.hg_joint_centers(_ptr(joints), _ptr(vis), _ptr(mu), _ptr(wt), b, j, int(heatmap_size[1]),
+                                   int(heatmap_size[0]), int(image_size[0]), int(image_size[1]), int(sigma * 3), _stream()),
+              "hg_joint_centers")
+    return mu, wt
+
+
+def gaussian_target(mu: torch.Tensor, weight: torch.Tensor, heatmap_size, sigma=1) -> torch.Tensor:
+    _require_cuda(mu, weight)
+    b, j = weight.shape
+    w, h = int(heatmap_size[0]), int(heatmap_size[1])
+    patch = gaussian_patch(sigma, mu.device)
+    tgt = torch.empty((b, j, h, w), dtype=torch.float32, device=mu.device)
+    lib.check(lib.hg_gaussian_target(_ptr(mu), _ptr(weight), _ptr(patch), _ptr(tgt), b, j, h, w, int(sigma * 3), _stream()),
+              "hg_gaussian_target")
+    return tgt
+
+
+def jmse_loss(preds: Sequence[torch.Tensor], target: Optional[torch.Tensor], target_weight: Optional[torch.Tensor],
+              *, want_grad: bool, grad_scale: float = 1.0, mu: Optional[torch.Tensor] = None, sigma=1):
+    """Fused JointsMSE over all stacks.  Returns (loss fp32 [1] device tensor, [grad per stack] or None)."""
+    preds = [p if (p.dtype == torch.float32 and p.is_contiguous()) else p.float().contiguous() for p in preds]
+    _require_cuda(*preds, target, target_weight, mu)
+    b, j, h, w = preds[0].shape
+    S = len(preds)
+    grads = [torch.empty_like(p) for p in preds] if want_grad else None
+    loss = torch.zeros(1, dtype=torch.float32, device=preds[0].device)
+    parr = (C.c_void_p * S)(*[p.data_ptr() for p in preds])
+    garr = (C.c_void_p * S)(*[g.data_ptr() for g in grads]) if want_grad else None
+    tw = target_weight.reshape(b, j).float().contiguous() if target_weight is not None else None
+    patch = gaussian_patch(sigma, preds[0].device) if target is None else None
+    lib.check(lib.hg_jmse_loss(parr, garr, _ptr(target), _ptr(tw), _ptr(mu), _ptr(patch), int(sigma * 3), _ptr(loss), S,
+                               b, j, h, w, C.c_float(grad_scale), _stream()), "hg_jmse_loss")
+    return loss, grads

@@ -1,0 +1,150 @@
+/*
+ * hg_api.h -- C ABI of libhgb200.so: hand-written sm_100a kernels for the stacked-hourglass
+ * hot path of minhhoangbui/hourglass-pose-estimation.
+ *
+ * The reference has NO native interface for this path: everything is Python calling into
+ * PyTorch/cuDNN.  The boundary therefore sits one level down: each entry
+ * point below replaces the library op(s) a reference call site issues, takes raw DEVICE pointers
+ * with explicit shapes, and is bound from the reference-facing Python modules with ctypes
+ * (hourglass-pose-estimation_b200/hgb200/_lib.py; stub shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - every function returns 0 (HG_OK) or a negative HG_ERR_* code; text via hg_last_error().
+ *   - never allocates device memory, never synchronises; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - the caller (PyTorch) owns every buffer; device = the calling thread's current device.
+ *   - activations are NHWC bf16 unless stated; heat maps / images at the API edge are NCHW fp32
+ *     exactly as the reference's tensors are.
+ *   - thread-safe: no mutable global state except a per-device property cache behind a mutex.
+ */
+#ifndef HG_API_H_
+#define HG_API_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_OK 0
+#define HG_ERR_INVALID (-1)  /* bad argument / unsupported shape */
+#define HG_ERR_CUDA (-2)     /* a CUDA runtime/driver call failed */
+#define HG_ERR_ARCH (-3)     /* device is not sm_100 */
+#define HG_ERR_DEVICE (-4)   /* a kernel reported a protocol timeout through its error word */
+
+#define HG_API_VERSION 1
+
+int hg_api_version(void);
+/* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
+size_t hg_last_error(char* buf, size_t cap);
+/* 0 if the current device can run the library (compute capability 10.x). */
+int hg_check_device(void);
+/* Device-side error word: kernels with bounded mbarrier waits write a non-zero code here when a
+ * wait times out instead of hanging.  The word lives in caller-owned device memory (4 bytes). */
+
+/* ------------------------------------------------------------------------------------------- *
+ * Convolution as implicit GEMM on tcgen05/TMEM (replaces nn.Conv2d + folded nn.BatchNorm2d +
+ * nn.ReLU + residual add + nearest-upsample add:  src/models/modules.py:27-47,80-96 and
+ * src/models/hourglass.py:60-67,71-73,83-89 of the reference).
+ *
+ *   out[n,y,x,:] = epi( sum_taps  W[:, tap, :] . pro(in[n, y+dy, x+dx, :])
+ *                       + W2 . in2[n,y,x,:] + bias )
+ *   pro(v)  = relu(v * in_scale[c] + in_shift[c])          if in_scale != NULL (pre-activation bn1)
+ *   epi(a)  = [relu]( a + residual[n,y,x,:] + up_low[n, y/2, x/2, :] )   (each term optional)
+ *
+ * weight: bf16 [cout_pad][ktot], K-major, ktot = taps*cin + cin2, k = tap*cin + c (tap = ky*3+kx),
+ *         then the cin2 columns of the second (1x1) operand; cout_pad = cout rounded up to 16.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hg_conv_desc {
+    const void* in;          /* bf16 NHWC [n][h][w][cin]                                        */
+    const void* in2;         /* optional second 1x1 operand, bf16 NHWC [n][h][w][cin2], or NULL  */
+    const void* weight;      /* bf16 [cout_pad][ktot]                                           */
+    const float* bias;       /* fp32 [cout_pad]                                                 */
+    const float* in_scale;   /* fp32 [cin] or NULL (prologue on `in`; 1x1 only)                 */
+    const float* in_shift;   /* fp32 [cin] or NULL                                              */
+    const void* residual;    /* bf16 NHWC [n][h][w][cout] or NULL                               */
+    const void* up_low;      /* bf16 NHWC [n][h/2][w/2][cout] or NULL (nearest x2 then add)     */
+    void* out;               /* bf16 NHWC [n][h][w][cout]      (NULL when out_nchw_f32 is used) */
+    float* out_nchw_f32;     /* fp32 NCHW [n][cout][h][w] heat-map output (cout_pad <= 32 only) */
+    unsigned int* err_word;  /* device uint32, set non-zero on a kernel protocol timeout         */
+    int32_t n, h, w;
+    int32_t cin, cin2, cout;
+    int32_t ksize;           /* 1 or 3 (stride 1, pad ksize/2)                                  */
+    int32_t relu;            /* apply ReLU in the epilogue                                      */
+} hg_conv_desc;
+
+int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream);
+
+/* Stem: conv 7x7 stride 2 pad 3 (3 -> cout) + folded BN + ReLU (src/models/hourglass.py:71-73).
+ * Step 1 gathers NCHW fp32 pixels into K-major bf16 rows [n*oh*ow][192] (k = (ky*7+kx)*3 + c,
+ * zero padded 147 -> 192); flip_w != 0 reads the image mirrored left-right (flip test).
+ * Step 2 is hg_conv_nhwc_bf16 with ksize 1, cin 192 on that matrix. */
+int hg_stem_im2col(const float* in_nchw, void* out_rows, int32_t n, int32_t h, int32_t w, int32_t flip_w,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * Bandwidth-bound NHWC bf16 ops
+ * ------------------------------------------------------------------------------------------- */
+/* F.max_pool2d(x, 2, stride=2)  -- src/models/modules.py:82, src/models/hourglass.py:76 */
+int hg_maxpool2x2_nhwc(const void* in, void* out, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
+/* out = a + nearest_upsample_x2(low)  -- src/models/modules.py:90,95 (stand-alone form) */
+int hg_upsample2x_add_nhwc(const void* a, const void* low, void* out, int32_t n, int32_t h, int32_t w, int32_t c,
+                           void* stream);
+/* out = relu(x*scale[c] + shift[c])  -- eval BatchNorm2d + ReLU (stand-alone form of the prologue) */
+int hg_bn_relu_nhwc(const void* in, const float* scale, const float* shift, void* out, int64_t pixels, int32_t c,
+                    void* stream);
+/* layout converters at the API edge */
+int hg_nchw_f32_to_nhwc_bf16(const float* in, void* out, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+int hg_nhwc_bf16_to_nchw_f32(const void* in, float* out, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * Heat-map decode  (src/utils/evaluation.py:8-27, src/utils/inference.py:48-67,
+ *                   src/utils/transforms.py:32-94)
+ * ------------------------------------------------------------------------------------------- */
+/* get_preds: hm fp32 [b][j][h][w] -> preds fp32 [b][j][2] (quirk coords, masked by maxval>0),
+ * maxval fp32 [b][j] (may be NULL), flat argmax int32 [b][j] (may be NULL; first max wins). */
+int hg_decode_argmax(const float* hm, float* preds, float* maxval, int32_t* argidx, int32_t b, int32_t j, int32_t h,
+                     int32_t w, void* stream);
+/* get_final_preds_v1 applied to EVERY batch element: argmax + quarter-pixel sign shift + inverse
+ * affine.  center/scale: fp64 [b][2]; out: fp64 [b][j][2].  out_w/out_h = `output_size`. */
+int hg_decode_final_preds(const float* hm, const double* center, const double* scale, double* out, int32_t b,
+                          int32_t j, int32_t h, int32_t w, int32_t out_w, int32_t out_h, void* stream);
+/* flip-test merge (defined from the reference's flip_pairs):
+ * out[b][k] = 0.5*(hm[b][k] + mirror_w(hm_flip[b][perm[k]])) ; perm: int32 [j] on the device. */
+int hg_flip_average(const float* hm, const float* hm_flip, const int32_t* perm, float* out, int32_t b, int32_t j,
+                    int32_t h, int32_t w, void* stream);
+/* PCK on heat maps (accuracy(), src/utils/evaluation.py:30-76), device part: per (b,j) normalised
+ * distance or -1 -> dists fp32 [j][b]; the tiny per-joint averaging stays on the host. */
+int hg_pck_dists(const float* out_hm, const float* tgt_hm, float* dists, int32_t b, int32_t j, int32_t h, int32_t w,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * JointsMSE loss (src/loss/mse.py:14-44) and Gaussian targets (src/datasets/common.py:197-248)
+ * ------------------------------------------------------------------------------------------- */
+#define HG_MAX_STACKS 16
+
+/* Per-joint Gaussian centres: mu int32 [b][j][2] = (int(x/stride_x + .5), int(y/stride_y + .5)) with
+ * C truncation, weight fp32 [b][j] = vis[..,0], forced to 0 when the (2r+1)^2 patch is entirely off the
+ * map (common.py:217-227).  joints/vis: fp64 [b][j][3] in input-pixel coordinates. */
+int hg_joint_centers(const double* joints, const double* vis, int32_t* mu, float* weight, int32_t b, int32_t j,
+                     int32_t h, int32_t w, int32_t in_w, int32_t in_h, int32_t radius, void* stream);
+/* target fp32 [b][j][h][w]: the (2r+1)x(2r+1) `patch` (device fp32, row-major; the host fills it with
+ * exp(-((x-r)^2+(y-r)^2)/(2 sigma^2)) exactly as the reference's numpy does) pasted at mu, clipped, for
+ * joints with weight > 0.5; zero elsewhere (common.py:229-246). */
+int hg_gaussian_target(const int32_t* mu, const float* weight, const float* patch, float* target, int32_t b,
+                       int32_t j, int32_t h, int32_t w, int32_t radius, void* stream);
+/* loss = sum_s 1/(2*J*B*h*w) sum_{b,j,hw} (w*p - w*g)^2  accumulated into loss_out (device fp32[1],
+ * zeroed by the caller); grad[s] = w^2 (p-g)/(J*B*h*w) * grad_scale.
+ * preds/grads: HOST arrays of `stacks` device pointers to fp32 [b][j][h][w] (grads may be NULL).
+ * target_weight: fp32 [b][j] or NULL (use_target_weight=False).
+ * The target is either `target` (fp32 [b][j][h][w]) or, when target == NULL, generated on the fly from
+ * (mu, patch, radius) with the visibility rule of hg_gaussian_target applied to `target_weight`. */
+int hg_jmse_loss(const float* const* preds, float* const* grads, const float* target, const float* target_weight,
+                 const int32_t* mu, const float* patch, int32_t radius, float* loss_out, int32_t stacks, int32_t b,
+                 int32_t j, int32_t h, int32_t w, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HG_API_H_ */

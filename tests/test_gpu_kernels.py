@@ -1,0 +1,211 @@
+"""GPU parity tests of the individual kernels, through the C ABI (ctypes), against the CPU oracle,
+the golden fixtures minted from the live reference, and plain torch fp32 references."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import decode_oracle as D
+from oracle import loss_oracle as L
+from oracle import golden_inputs as GI
+from tests.gpu_cases import CONV_CASES, make_conv_case, conv_reference, run_conv_case, no_tf32, r16
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from hgb200 import ops as _ops, lib
+    lib.check(lib.hg_check_device(), "hg_check_device")
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------ convolutions
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_gemm(case, ops, dev):
+    t = make_conv_case(case, dev)
+    ref = conv_reference(t)
+    out = run_conv_case(t)
+    scale = float(ref.abs().max())
+    # bf16 output rounding (2^-8 relative) + fp32 accumulation-order noise; fp32 heads are tighter
+    tol = scale * (1e-3 if t["heads"] else 2 ** -7)
+    assert torch.isfinite(out).all()
+    err = float((out - ref).abs().max())
+    assert err <= tol, f"{case[0]}: max abs err {err} > {tol} (scale {scale})"
+
+
+def test_conv_rejects_bad_shapes(ops, dev):
+    from hgb200 import HgError
+    x = torch.zeros(1, 8, 8, 48, dtype=torch.bfloat16, device=dev)
+    w = torch.zeros(64, 48, dtype=torch.bfloat16, device=dev)
+    b = torch.zeros(64, device=dev)
+    with pytest.raises(HgError):
+        ops.conv_nhwc(x, w, b, ksize=1, cout=64)          # cin not a multiple of 64
+
+
+def test_stem_im2col_and_gemm(ops, dev):
+    no_tf32()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 64, 96, generator=g)
+    wt = torch.randn(64, 3, 7, 7, generator=g) / 12.0
+    bias = torch.randn(64, generator=g) * 0.1
+    for flip in (False, True):
+        rows = ops.stem_im2col(x.to(dev), flip_w=flip)
+        assert rows.shape == (2, 32, 48, 192)
+        wmat = torch.zeros(64, 192)
+        wmat[:, :147] = wt.permute(0, 2, 3, 1).reshape(64, 147)
+        out = ops.conv_nhwc(rows, wmat.to(torch.bfloat16).to(dev), bias.to(dev), ksize=1, cout=64, relu=True)
+        torch.cuda.synchronize()
+        ops.check_err_word(dev)
+        xin = x.flip(-1) if flip else x
+        ref = F.relu(F.conv2d(r16(xin).to(dev), r16(wt).to(dev), bias.to(dev), stride=2, padding=3))
+        err = float((out.float().permute(0, 3, 1, 2) - ref).abs().max())
+        assert err <= float(ref.abs().max()) * 2 ** -7
+
+
+# ------------------------------------------------------------------------------------------ bandwidth kernels
+@pytest.mark.parametrize("shape", [(2, 64, 64, 256), (3, 8, 8, 128), (1, 4, 6, 64), (5, 2, 2, 256)])
+def test_maxpool_bit_exact(shape, ops, dev):
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).to(dev)
+    out = ops.maxpool2x2(x)
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 2, stride=2).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 256), (3, 8, 8, 128), (1, 4, 6, 64)])
+def test_upsample_add_bit_exact(shape, ops, dev):
+    g = torch.Generator().manual_seed(2)
+    n, h, w, c = shape
+    a = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).to(dev)
+    low = torch.randn(n, h // 2, w // 2, c, generator=g).to(torch.bfloat16).to(dev)
+    out = ops.upsample2x_add(a, low)
+    up = F.interpolate(low.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    ref = (a.float() + up).to(torch.bfloat16)
+    assert torch.equal(out, ref)
+
+
+def test_bn_relu(ops, dev):
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 7, 5, 128, generator=g).to(torch.bfloat16).to(dev)
+    s = (0.5 + torch.rand(128, generator=g)).to(dev)
+    t = torch.randn(128, generator=g).to(dev)
+    out = ops.bn_relu(x, s, t)
+    ref = F.relu(torch.addcmul(t, x.float(), s)).to(torch.bfloat16)      # fma, one rounding
+    assert (out.float() - ref.float()).abs().max() <= 2 ** -7 * ref.float().abs().max()
+    assert (out == ref).float().mean() > 0.99
+
+
+def test_layout_roundtrip(ops, dev):
+    x = torch.randn(2, 24, 6, 10, generator=torch.Generator().manual_seed(5)).to(dev)
+    nhwc = ops.nchw_to_nhwc_bf16(x)
+    assert torch.equal(nhwc, x.permute(0, 2, 3, 1).to(torch.bfloat16))
+    back = ops.nhwc_bf16_to_nchw(nhwc)
+    assert torch.equal(back, x.to(torch.bfloat16).float())
+
+
+# ------------------------------------------------------------------------------------------ decode (bit-exact)
+def test_decode_argmax_golden_bit_exact(ops, dev):
+    z = np.load(os.path.join(GOLDEN, "decode.npz"))
+    for i, hm in enumerate(GI.heatmap_cases()):
+        preds, maxval, idx = ops.decode_argmax(torch.from_numpy(hm).to(dev))
+        np.testing.assert_array_equal(preds.cpu().numpy(), z[f"preds{i}"])          # reference output
+        np.testing.assert_array_equal(preds.cpu().numpy(), D.get_preds(hm))         # oracle
+        flat = hm.reshape(hm.shape[0], hm.shape[1], -1)
+        np.testing.assert_array_equal(idx.cpu().numpy(), flat.argmax(2).astype(np.int32))
+        np.testing.assert_array_equal(maxval.cpu().numpy(), flat.max(2))
+
+
+def test_decode_argmax_random_with_ties(ops, dev):
+    rng = np.random.RandomState(0)
+    for (b, j, h, w) in [(128, 16, 64, 64), (7, 17, 64, 48), (3, 5, 7, 9), (2, 3, 1, 1), (64, 21, 16, 16)]:
+        # few distinct values -> many ties; first flat index must win
+        hm = rng.randint(-3, 4, size=(b, j, h, w)).astype(np.float32)
+        preds, _, idx = ops.decode_argmax(torch.from_numpy(hm).to(dev))
+        np.testing.assert_array_equal(idx.cpu().numpy(), hm.reshape(b, j, -1).argmax(2).astype(np.int32))
+        np.testing.assert_array_equal(preds.cpu().numpy(), D.get_preds(hm))
+
+
+def test_decode_final_preds_golden(ops, dev):
+    z = np.load(os.path.join(GOLDEN, "decode.npz"))
+    cases = GI.heatmap_cases()
+    centers, scales = GI.decode_args(cases)
+    for i, hm in enumerate(cases):
+        B, J, H, W = hm.shape
+        out = ops.decode_final_preds(torch.from_numpy(hm).to(dev), centers[i], scales[i], (W, H)).cpu().numpy()
+        # quarter-pixel offsets are exact; the float64 affine is solved by Cramer instead of cv2's LU
+        np.testing.assert_allclose(out, z[f"final{i}"], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(out, D.get_final_preds_batch(hm, centers[i], scales[i], (W, H)), rtol=0, atol=1e-9)
+
+
+def test_flip_average(ops, dev):
+    rng = np.random.RandomState(1)
+    for J, pairs, (H, W) in [(16, D.MPII_FLIP_PAIRS, (64, 64)), (17, D.COCO_FLIP_PAIRS, (64, 48))]:
+        hm = rng.randn(3, J, H, W).astype(np.float32)
+        hf = rng.randn(3, J, H, W).astype(np.float32)
+        perm = torch.from_numpy(D.flip_perm(J, pairs).astype(np.int32)).to(dev)
+        out = ops.flip_average(torch.from_numpy(hm).to(dev), torch.from_numpy(hf).to(dev), perm)
+        np.testing.assert_array_equal(out.cpu().numpy(), D.flip_average(hm, hf, pairs))
+
+
+def test_pck_dists(ops, dev):
+    for pred, tgt in GI.accuracy_cases():
+        d = ops.pck_dists(torch.from_numpy(pred).to(dev), torch.from_numpy(tgt).to(dev)).cpu().numpy()
+        B, J = pred.shape[:2]
+        p, g = D.get_preds(pred), D.get_preds(tgt)
+        norm = np.float32(pred.shape[3]) / np.float32(10)
+        for b in range(B):
+            for j in range(J):
+                if g[b, j, 0] > 1 and g[b, j, 1] > 1:
+                    e = p[b, j] - g[b, j]
+                    ref = np.float32(np.sqrt(np.float32(e[0] * e[0] + e[1] * e[1]))) / norm
+                    assert abs(d[j, b] - ref) <= 1e-6 * max(1.0, abs(ref))
+                else:
+                    assert d[j, b] == -1
+
+
+# ------------------------------------------------------------------------------------------ targets + loss
+def test_gaussian_target_bit_exact(ops, dev):
+    z = np.load(os.path.join(GOLDEN, "loss.npz"))
+    for i, c in enumerate(GI.loss_cases()):
+        joints = torch.from_numpy(c["joints"]).to(dev)
+        vis = torch.from_numpy(c["vis"]).to(dev)
+        mu, wt = ops.joint_centers(joints, vis, c["hsz"], c["isz"], sigma=1)
+        tgt = ops.gaussian_target(mu, wt, c["hsz"], sigma=1)
+        np.testing.assert_array_equal(wt.cpu().numpy()[..., None], z[f"tw{i}"])
+        np.testing.assert_array_equal(tgt.cpu().numpy(), z[f"target{i}"])
+
+
+@pytest.mark.parametrize("on_the_fly", [False, True])
+def test_jmse_loss_and_grad(on_the_fly, ops, dev):
+    z = np.load(os.path.join(GOLDEN, "loss.npz"))
+    stride = int(z["grad_stride"])
+    for i, c in enumerate(GI.loss_cases()):
+        tg, tw = z[f"target{i}"], z[f"tw{i}"]
+        preds = [torch.from_numpy(tg + n).to(dev) for n in c["noise"]]
+        twd = torch.from_numpy(tw).to(dev)
+        if on_the_fly:
+            mu, wt = ops.joint_centers(torch.from_numpy(c["joints"]).to(dev), torch.from_numpy(c["vis"]).to(dev),
+                                       c["hsz"], c["isz"], sigma=1)
+            loss, grads = ops.jmse_loss(preds, None, wt, want_grad=True, mu=mu, sigma=1)
+        else:
+            loss, grads = ops.jmse_loss(preds, torch.from_numpy(tg).to(dev), twd, want_grad=True)
+        ref = float(z[f"loss{i}"])
+        assert abs(float(loss.item()) - ref) <= 2e-5 * abs(ref)          # fp32 sums, different order
+        oloss, ograds = L.joints_mse([p.cpu().numpy() for p in preds], tg, tw, True)
+        assert abs(float(loss.item()) - oloss) <= 2e-5 * abs(oloss)
+        for s, g in enumerate(grads):
+            np.testing.assert_allclose(g.cpu().numpy().reshape(-1)[::stride], z[f"grad{i}_{s}"], rtol=2e-5, atol=1e-10)
+    # use_target_weight=False
+    c = GI.loss_cases()[0]
+    tg = z["target0"]
+    preds = [torch.from_numpy(tg + n).to(dev) for n in c["noise"]]
+    loss, _ = ops.jmse_loss(preds, torch.from_numpy(tg).to(dev), None, want_grad=False)
+    assert abs(float(loss.item()) - float(z["loss_nw0"])) <= 2e-5 * float(z["loss_nw0"])
