@@ -1,0 +1,241 @@
+"""Inference engine: the stacked-hourglass forward as a static plan of sm_100a kernel launches.
+
+A plan is built once per (batch, height, width, flip) from folded weights: every intermediate lives in
+a buffer handed out by a small arena (reused as soon as its last reader is enqueued -- single stream,
+so stream order makes reuse safe), every launch is a closure over fixed device pointers, and the
+whole sequence (~50 launches per stack) is captured into ONE CUDA graph so the host cost per
+forward is a single graph launch.
+
+Dataflow (reference: src/models/hourglass.py:69-90, src/models/modules.py:27-47,80-96):
+  stem     im2col(7x7/s2) -> GEMM(+folded bn1, ReLU)
+  block    K1: 1x1 GEMM, prologue relu(bn1(x)), epilogue +b (bn2 folded) ReLU
+           K2: 3x3 implicit GEMM (9 shifted TMA boxes), epilogue +b (bn3 folded) ReLU
+           K3: 1x1 GEMM, epilogue +b +residual [+ nearest-upsampled low-res branch]
+                (downsample blocks: residual conv rides along as a second K segment)
+  hourglass  low branch first; `up1 + upsample(low3)` is the up1 block's K3 epilogue
+  heads    fc (+folded BN, ReLU) -> score (fp32 NCHW heat map) ; remap = ONE merged 256->256 GEMM
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from ._lib import HgError
+from .fold import NetWeights, BlockWeights
+
+
+class _Arena:
+    def __init__(self, device):
+        self.device = device
+        self.free = defaultdict(list)
+        self.total_bytes = 0
+
+    def get(self, shape, dtype=torch.bfloat16) -> torch.Tensor:
+        key = (tuple(shape), dtype)
+        if self.free[key]:
+            return self.free[key].pop()
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        self.total_bytes += t.numel() * t.element_size()
+        return t
+
+    def put(self, t: torch.Tensor):
+        self.free[(tuple(t.shape), t.dtype)].append(t)
+
+
+class Plan:
+    """A recorded launch sequence with static buffers; `run()` replays it (graph or eager)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.launches: List[Callable[[], None]] = []
+        self.input: Optional[torch.Tensor] = None
+        self.outputs: List[torch.Tensor] = []
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.arena_bytes = 0
+
+    @property
+    def num_launches(self) -> int:
+        return len(self.launches)
+
+    def run_eager(self):
+        for fn in self.launches:
+            fn()
+
+    def capture(self):
+        # warm up on a side stream (lazy module loading, smem attribute opt-in), then capture
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.run_eager()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        ops.check_err_word(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run_eager()
+        self.graph = g
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run_eager()
+
+
+class HourglassEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, depth: int = 4):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise HgError("HourglassEngine needs a CUDA device (no CPU fallback)")
+        w = NetWeights(state_dict, depth)
+        self.w = w
+        self.num_stacks = w.num_stacks
+        self.num_classes = w.num_classes
+        self._to_device(w)
+        self.plans: Dict[Tuple[int, int, int, bool], Plan] = {}
+
+    def _to_device(self, obj):
+        for k, v in list(vars(obj).items()):
+            if torch.is_tensor(v):
+                setattr(obj, k, v.to(self.device).contiguous())
+            elif isinstance(v, (list, tuple)):
+                setattr(obj, k, self._conv_list(v))
+            elif isinstance(v, BlockWeights):
+                self._to_device(v)
+
+    def _conv_list(self, v):
+        out = []
+        for e in v:
+            if torch.is_tensor(e):
+                out.append(e.to(self.device).contiguous())
+            elif isinstance(e, (list, tuple)):
+                out.append(type(e)(self._conv_list(e)))
+            elif isinstance(e, BlockWeights):
+                self._to_device(e)
+                out.append(e)
+            else:
+                out.append(e)
+        return out
+
+    # ------------------------------------------------------------------ plan construction
+    def build_plan(self, n: int, h: int, w: int, flip: bool = False, use_graph: bool = True) -> Plan:
+        if h % 64 or w % 64:
+            raise HgError(f"input {h}x{w}: height and width must be multiples of 64 (4 pooling levels on H/4 x W/4)")
+        dev = self.device
+        W = self.w
+        plan = Plan(dev)
+        arena = _Arena(dev)
+        L = plan.launches
+        plan.input = torch.zeros((n, 3, h, w), dtype=torch.float32, device=dev)
+
+        def conv(x, wt, bias, *, ksize, cout, relu=False, in_scale=None, in_shift=None, residual=None, up_low=None,
+                 x2=None, out_f32=None):
+            shape = x.shape[:3]
+            if out_f32 is not None:
+                L.append(lambda: ops.conv_nhwc(x, wt, bias, ksize=ksize, cout=cout, relu=relu, heads=True,
+                                               out_nchw_f32=out_f32))
+                return out_f32
+            out = arena.get((*shape, cout))
+            L.append(lambda: ops.conv_nhwc(x, wt, bias, ksize=ksize, cout=cout, relu=relu, in_scale=in_scale,
+                                           in_shift=in_shift, residual=residual, up_low=up_low, x2=x2, out=out))
+            return out
+
+        def block(bw: BlockWeights, x, up_low=None):
+            a2 = conv(x, bw.w1, bw.b1, ksize=1, cout=bw.planes, relu=True, in_scale=bw.s1, in_shift=bw.t1)
+            a3 = conv(a2, bw.w2, bw.b2, ksize=3, cout=bw.planes, relu=True)
+            arena.put(a2)
+            if bw.downsample:
+                out = conv(a3, bw.w3, bw.b3, ksize=1, cout=bw.cout, x2=x, up_low=up_low)
+            else:
+                out = conv(a3, bw.w3, bw.b3, ksize=1, cout=bw.cout, residual=x, up_low=up_low)
+            arena.put(a3)
+            return out
+
+        def chain(blocks, x, up_low=None, keep_input=True):
+            """nn.Sequential of bottlenecks; `up_low` joins the LAST block's epilogue."""
+            cur = x
+            for i, bw in enumerate(blocks):
+                nxt = block(bw, cur, up_low if i == len(blocks) - 1 else None)
+                if cur is not x or not keep_input:
+                    arena.put(cur)
+                cur = nxt
+            return cur
+
+        def pool(x):
+            nb, hh, ww, c = x.shape
+            out = arena.get((nb, hh // 2, ww // 2, c))
+            L.append(lambda: ops.maxpool2x2(x, out))
+            return out
+
+        def hourglass(levels, d, x):
+            """Hourglass._hour_glass_forward(n=d+1, x); x stays owned by the caller."""
+            p = pool(x)
+            low1 = chain(levels[d][1], p, keep_input=False)
+            if d > 0:
+                low2 = hourglass(levels, d - 1, low1)
+                arena.put(low1)
+            else:
+                low2 = chain(levels[0][3], low1, keep_input=False)
+            low3 = chain(levels[d][2], low2, keep_input=False)
+            out = chain(levels[d][0], x, up_low=low3)
+            arena.put(low3)
+            return out
+
+        # ---- stem
+        rows = arena.get((n, h // 2, w // 2, 192))
+        x_in = plan.input
+        L.append(lambda: ops.stem_im2col(x_in, flip_w=flip, out=rows))
+        s0 = conv(rows, W.stem_w, W.stem_b, ksize=1, cout=64, relu=True)
+        arena.put(rows)
+        l1 = chain(W.layer1, s0, keep_input=False)
+        p1 = pool(l1)
+        arena.put(l1)
+        l2 = chain(W.layer2, p1, keep_input=False)
+        x = chain(W.layer3, l2, keep_input=False)
+        # ---- stacks
+        hm_h, hm_w = h // 4, w // 4
+        for i in range(self.num_stacks):
+            y = hourglass(W.hg[i], W.depth - 1, x)
+            y = chain(W.res[i], y, keep_input=False)
+            fw, fb = W.fc[i]
+            y2 = conv(y, fw, fb, ksize=1, cout=256, relu=True)
+            arena.put(y)
+            out_i = torch.empty((n, self.num_classes, hm_h, hm_w), dtype=torch.float32, device=dev)
+            sw, sb = W.score[i]
+            conv(y2, sw, sb, ksize=1, cout=self.num_classes, out_f32=out_i)
+            plan.outputs.append(out_i)
+            if i < self.num_stacks - 1:
+                mw, mb = W.remap[i]
+                x_next = conv(y2, mw, mb, ksize=1, cout=256, residual=x)
+                arena.put(x)
+                x = x_next
+            arena.put(y2)
+        plan.arena_bytes = arena.total_bytes
+        if use_graph:
+            plan.capture()
+        return plan
+
+    def plan_for(self, n, h, w, flip=False, use_graph=True) -> Plan:
+        key = (n, h, w, bool(flip), bool(use_graph))
+        p = self.plans.get(key)
+        if p is None:
+            p = self.build_plan(n, h, w, flip, use_graph)
+            self.plans[key] = p
+        return p
+
+    # ------------------------------------------------------------------ public
+    def forward(self, x: torch.Tensor, flip: bool = False, use_graph: bool = True, clone: bool = True):
+        """x: fp32 NCHW [n,3,h,w] on this device -> list of num_stacks fp32 NCHW heat maps [n,J,h/4,w/4].
+
+        With clone=False the returned tensors are the plan's static output buffers (overwritten by the
+        next forward of the same shape)."""
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise HgError(f"expected [n,3,h,w], got {tuple(x.shape)}")
+        n, _, h, w = x.shape
+        plan = self.plan_for(n, h, w, flip, use_graph)
+        plan.input.copy_(x, non_blocking=True)
+        plan.run()
+        return [o.clone() for o in plan.outputs] if clone else list(plan.outputs)
