@@ -23,6 +23,8 @@ int check_cuda(cudaError_t e, const char* what);   // returns 0 or HG_ERR_CUDA a
 
 int num_sms();   // SM count of the current device (cached per device)
 
+
+
 // ----------------------------------------------------------------------------------------------
 // small device utilities
 // ----------------------------------------------------------------------------------------------
@@ -118,6 +120,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                      reinterpret_cast<uint64_t>(m)),
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -1,0 +1,513 @@
+// 1x1 convolution (pixel-major GEMM) for NHWC bf16 activations -- the HBM-bound half of the hourglass
+// (conv1 / conv3 of every bottleneck, fc, merged remap).  Second-generation kernel, specialised for
+// streaming: every byte of A, residual and output crosses HBM exactly once and nothing else does.
+//
+//   * weights [BLOCK_N x K] are loaded ONCE per persistent CTA and stay resident in shared memory
+//     (<= 128 KiB); the main-loop ring carries only 16 KiB A slabs, so it is 4-8 stages deep.
+//   * the residual tile (and the quarter-resolution tensor of the fused nearest-upsample add) are
+//     prefetched by TMA into the SAME swizzled staging slabs the epilogue later overwrites with the
+//     result and TMA-stores: no per-thread global loads anywhere in the epilogue.
+//   * pre-activation bn1+ReLU prologue with a conflict-free mapping (a quarter-warp owns one
+//     128-byte row; per-thread channel chunk is fixed so scale/shift live in registers per k-block).
+//
+// Warp roles: 0 = A producer (TMA), 1 = MMA issuer + TMEM owner, 2 = staging-ring producer (TMA),
+//             3 = idle, 4..7 = epilogue, 8..11 = prologue (optional).
+#include "hg_common.cuh"
+#include "../../include/hg_api.h"
+
+#include <cudaTypedefs.h>
+#include <cstring>
+#include <mutex>
+
+namespace hg {
+
+namespace c1 {
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;
+constexpr int kSlabBytes = kTileM * kBlockK * 2;     // 16 KiB: one [128 x 64] bf16 slab (A stage or staging slab)
+constexpr int kUpRows = 32;                          // quarter-resolution pixels under one 128-pixel tile
+constexpr int kUpBytes = kUpRows * kBlockK * 2;      // 4 KiB
+constexpr int kMaxAStages = 8;
+constexpr int kMaxRing = 6;
+constexpr int kMaxK = 512;
+constexpr int kSmemLimit = 232448;
+
+struct Params {
+    CUtensorMap map_a;      // (c, m) over `in`
+    CUtensorMap map_a2;     // (c, m) over `in2`
+    CUtensorMap map_b;      // (k, cout) over weights
+    CUtensorMap map_res;    // (c, m) over residual
+    CUtensorMap map_up;     // (c, m/4) over the quarter-resolution tensor
+    CUtensorMap map_out;    // (c, m) over out
+    const float* bias;
+    const float* in_scale;
+    const float* in_shift;
+    unsigned int* err_word;
+    int num_tiles;
+    int kb1, kb2;           // k-blocks from `in` / from `in2`
+    int cin;
+    int a_stages, ring;     // pipeline depths chosen by the host from the smem budget
+    int has_res, has_up, relu;
+};
+
+enum : uint32_t { kErrProducer = 0x1100, kErrMma = 0x1200, kErrRing = 0x1300, kErrEpilogue = 0x1400, kErrPrologue = 0x1500 };
+
+template <int BLOCK_N>
+__host__ __device__ constexpr int w_bytes(int num_kb) { return num_kb * BLOCK_N * kBlockK * 2; }
+
+template <int BLOCK_N, bool kPrologue>
+__global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const __grid_constant__ Params p) {
+    constexpr int kBStage = BLOCK_N * kBlockK * 2;
+    constexpr int kSlabs = BLOCK_N / 64;
+    constexpr int kTmemCols = 2 * BLOCK_N;           // 128 / 256 / 512
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int num_kb = p.kb1 + p.kb2;
+    uint8_t* smem_w = smem;                                        // num_kb x kBStage
+    uint8_t* smem_a = smem_w + num_kb * kBStage;                   // a_stages x 16 KiB
+    uint8_t* smem_ring = smem_a + p.a_stages * kSlabBytes;         // ring x 16 KiB
+    uint8_t* smem_up = smem_ring + p.ring * kSlabBytes;            // ring x 4 KiB (only if has_up)
+    float* s_bias = reinterpret_cast<float*>(smem_up + (p.has_up ? p.ring * kUpBytes : 0));
+    float* s_scale = s_bias + BLOCK_N;
+    float* s_shift = s_scale + (kPrologue ? kMaxK : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + (kPrologue ? kMaxK : 0));
+    uint64_t* full_bar = bars;                                     // [kMaxAStages]
+    uint64_t* empty_bar = full_bar + kMaxAStages;
+    uint64_t* ready_bar = empty_bar + kMaxAStages;
+    uint64_t* res_full_bar = ready_bar + kMaxAStages;              // [kMaxRing]
+    uint64_t* ring_empty_bar = res_full_bar + kMaxRing;
+    uint64_t* tmem_full_bar = ring_empty_bar + kMaxRing;           // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint64_t* w_bar = tmem_empty_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (kPrologue) {
+        for (int i = threadIdx.x; i < p.cin; i += blockDim.x) {
+            s_scale[i] = p.in_scale[i];
+            s_shift[i] = p.in_shift[i];
+        }
+    }
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&p.map_a);
+        tma_prefetch_desc(&p.map_b);
+        tma_prefetch_desc(&p.map_out);
+        if (p.kb2) tma_prefetch_desc(&p.map_a2);
+        if (p.has_res) tma_prefetch_desc(&p.map_res);
+        if (p.has_up) tma_prefetch_desc(&p.map_up);
+        for (int s = 0; s < kMaxAStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&ready_bar[s], 4);
+        }
+        for (int s = 0; s < kMaxRing; ++s) {
+            mbar_init(&res_full_bar[s], 1);
+            mbar_init(&ring_empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);
+        }
+        mbar_init(w_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp_idx == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp_idx == 0) {
+        // ===================== A producer: resident weights once, then the A slab stream =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(num_kb * kBStage));
+            for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem_w + kb * kBStage, &p.map_b, w_bar, kb * kBlockK, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+                const int m0 = tile * kTileM;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ok = mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_word, kErrProducer | 1);
+                    if (!ok) break;
+                    mbar_arrive_expect_tx(&full_bar[stage], kSlabBytes);
+                    if (kb < p.kb1)
+                        tma_load_2d(smem_a + stage * kSlabBytes, &p.map_a, &full_bar[stage], kb * kBlockK, m0);
+                    else
+                        tma_load_2d(smem_a + stage * kSlabBytes, &p.map_a2, &full_bar[stage], (kb - p.kb1) * kBlockK, m0);
+                    if (++stage == p.a_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BLOCK_N);
+            bool ok = mbar_wait(w_bar, 0, p.err_word, kErrMma | 3);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1u;
+                ok = mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u, p.err_word, kErrMma | 1);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ok = mbar_wait(kPrologue ? &ready_bar[stage] : &full_bar[stage], phase, p.err_word, kErrMma | 2);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + stage * kSlabBytes));
+                    const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_w + kb * kBStage));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        tc_mma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(&empty_bar[stage]);
+                    if (kb == num_kb - 1) tc_commit(&tmem_full_bar[acc]);
+                    if (++stage == p.a_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 2) {
+        // ===================== staging-ring producer: residual / upsample operands by TMA =====================
+        if (lane == 0) {
+            int buf = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            const uint32_t tx = static_cast<uint32_t>((p.has_res ? kSlabBytes : 0) + (p.has_up ? kUpBytes : 0));
+            for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+                const int m0 = tile * kTileM;
+                for (int slab = 0; slab < kSlabs; ++slab) {
+                    ok = mbar_wait(&ring_empty_bar[buf], phase ^ 1u, p.err_word, kErrRing | 1);
+                    if (!ok) break;
+                    if (tx != 0) {
+                        mbar_arrive_expect_tx(&res_full_bar[buf], tx);
+                        if (p.has_res)
+                            tma_load_2d(smem_ring + buf * kSlabBytes, &p.map_res, &res_full_bar[buf], slab * 64, m0);
+                        if (p.has_up)
+                            tma_load_2d(smem_up + buf * kUpBytes, &p.map_up, &res_full_bar[buf], slab * 64, m0 >> 2);
+                    } else {
+                        mbar_arrive(&res_full_bar[buf]);       // nothing to fetch: the slab is simply free
+                    }
+                    if (++buf == p.ring) {
+                        buf = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp_idx >= 4 && warp_idx < 8) {
+        // ===================== epilogue =====================
+        const int q = warp_idx & 3;
+        const int row = q * 32 + lane;
+        const bool leader = (warp_idx == 4 && lane == 0);
+        // quarter-resolution row under this pixel: tiles are 128-aligned runs of whole 2x2 blocks, so the
+        // 32 low-res pixels of a tile are contiguous; row r=(y,x) within the tile maps to (y/2, x/2).
+        // With W = 2^k <= 64:  r = yy*W + x  ->  low = (yy/2)*(W/2) + x/2
+        int low_row = 0;
+        if (p.has_up) {
+            const int W = p.has_up;            // has_up carries the image width
+            const int yy = row / W, x = row - yy * W;
+            low_row = (yy >> 1) * (W >> 1) + (x >> 1);
+        }
+        int it = 0;
+        int buf = 0;
+        uint32_t ring_phase = 0;
+        int prev_buf = -1;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1u;
+            const int m0 = tile * kTileM;
+            ok = mbar_wait(&tmem_full_bar[acc], acc_phase, p.err_word, kErrEpilogue | 1);
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+            for (int slab = 0; slab < kSlabs; ++slab) {
+                ok = mbar_wait(&res_full_bar[buf], ring_phase, p.err_word, kErrEpilogue | 2);
+                if (!ok) break;
+                uint8_t* stg = smem_ring + buf * kSlabBytes + row * 128;
+                const uint8_t* upb = smem_up + buf * kUpBytes + low_row * 128;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int col0 = slab * 64 + half * 32;
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + col0, v);
+                    uint4 r_res[4], r_up[4];
+                    if (p.has_res) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            r_res[i] = *reinterpret_cast<const uint4*>(stg + (((half * 4 + i) ^ (row & 7)) << 4));
+                    }
+                    if (p.has_up) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            r_up[i] = *reinterpret_cast<const uint4*>(upb + (((half * 4 + i) ^ (low_row & 7)) << 4));
+                    }
+                    tmem_ld_wait();
+                    if (slab == kSlabs - 1 && half == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                    }
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + s_bias[col0 + i];
+                    if (p.has_res) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t w4[4] = {r_res[i].x, r_res[i].y, r_res[i].z, r_res[i].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                f[i * 8 + 2 * j] += bf16_lo_to_f32(w4[j]);
+                                f[i * 8 + 2 * j + 1] += bf16_hi_to_f32(w4[j]);
+                            }
+                        }
+                    }
+                    if (p.has_up) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t w4[4] = {r_up[i].x, r_up[i].y, r_up[i].z, r_up[i].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                f[i * 8 + 2 * j] += bf16_lo_to_f32(w4[j]);
+                                f[i * 8 + 2 * j + 1] += bf16_hi_to_f32(w4[j]);
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 o;
+                        o.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]);
+                        o.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+                        o.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]);
+                        o.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+                        *reinterpret_cast<uint4*>(stg + (((half * 4 + i) ^ (row & 7)) << 4)) = o;
+                    }
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (leader) {
+                    tma_store_2d(&p.map_out, smem_ring + buf * kSlabBytes, slab * 64, m0);
+                    tma_store_commit();
+                    if (prev_buf >= 0) {
+                        tma_store_wait_read<1>();               // the previous slab's store has drained its smem
+                        mbar_arrive(&ring_empty_bar[prev_buf]);
+                    }
+                }
+                prev_buf = buf;
+                if (++buf == p.ring) {
+                    buf = 0;
+                    ring_phase ^= 1u;
+                }
+            }
+        }
+        if (leader) tma_store_wait<0>();
+    } else if (kPrologue && warp_idx >= 8) {
+        // ===================== prologue: a = relu(a*scale + shift), in place =====================
+        const int w = warp_idx - 8;
+        const int c = lane & 7;                 // logical 16-byte chunk = 8 channels, fixed per thread
+        const int rsub = lane >> 3;
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ok = mbar_wait(&full_bar[stage], phase, p.err_word, kErrPrologue | 1);
+                if (!ok) break;
+                if (kb < p.kb1) {
+                    const int c0 = kb * kBlockK + c * 8;
+                    const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c0);
+                    const float4 s1 = *reinterpret_cast<const float4*>(s_scale + c0 + 4);
+                    const float4 h0 = *reinterpret_cast<const float4*>(s_shift + c0);
+                    const float4 h1 = *reinterpret_cast<const float4*>(s_shift + c0 + 4);
+                    uint8_t* a_base = smem_a + stage * kSlabBytes;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 16 + w * 4 + rsub;           // a quarter-warp owns one 128-byte row
+                        uint4* ptr = reinterpret_cast<uint4*>(a_base + row * 128 + ((c ^ (row & 7)) << 4));
+                        uint4 d = *ptr;
+                        d.x = pack_bf16x2(fmaxf(fmaf(bf16_lo_to_f32(d.x), s0.x, h0.x), 0.f),
+                                          fmaxf(fmaf(bf16_hi_to_f32(d.x), s0.y, h0.y), 0.f));
+                        d.y = pack_bf16x2(fmaxf(fmaf(bf16_lo_to_f32(d.y), s0.z, h0.z), 0.f),
+                                          fmaxf(fmaf(bf16_hi_to_f32(d.y), s0.w, h0.w), 0.f));
+                        d.z = pack_bf16x2(fmaxf(fmaf(bf16_lo_to_f32(d.z), s1.x, h1.x), 0.f),
+                                          fmaxf(fmaf(bf16_hi_to_f32(d.z), s1.y, h1.y), 0.f));
+                        d.w = pack_bf16x2(fmaxf(fmaf(bf16_lo_to_f32(d.w), s1.z, h1.z), 0.f),
+                                          fmaxf(fmaf(bf16_hi_to_f32(d.w), s1.w, h1.w), 0.f));
+                        *ptr = d;
+                    }
+                    fence_proxy_async_smem();
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready_bar[stage]);
+                if (++stage == p.a_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static std::mutex mu;
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+            set_last_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+            return nullptr;
+        }
+        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+// row-major bf16 matrix [rows][cols] viewed as (cols, rows); box (64, box_rows), 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+    auto enc = encode_fn();
+    if (!enc) return HG_ERR_CUDA;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (cols %llu rows %llu box_rows %u)", (int)r,
+                       (unsigned long long)cols, (unsigned long long)rows, box_rows);
+        return HG_ERR_CUDA;
+    }
+    return HG_OK;
+}
+
+template <int BLOCK_N, bool kPrologue>
+static int launch(const Params& kp, int smem_bytes, cudaStream_t stream) {
+    auto kern = conv1x1_kernel<BLOCK_N, kPrologue>;
+    static std::mutex mu;
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    HG_CUDA_OK(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 64 || !(done_mask >> dev & 1ull)) {
+            HG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            if (dev < 64) done_mask |= 1ull << dev;
+        }
+    }
+    const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+    kern<<<grid, kPrologue ? 384 : 256, smem_bytes, stream>>>(kp);
+    HG_CUDA_OK(cudaGetLastError());
+    return HG_OK;
+}
+
+}  // namespace c1
+
+// Returns 1 if this kernel can run the descriptor, 0 if the generic kernel must be used.
+int conv1x1_supported(const hg_conv_desc* d) {
+    if (d->ksize != 1 || d->out_nchw_f32 != nullptr || d->out == nullptr) return 0;
+    if (d->cout != 64 && d->cout != 128 && d->cout != 256) return 0;
+    const int k = d->cin + d->cin2;
+    if (k > c1::kMaxK || static_cast<long long>(k) * d->cout * 2 > 128 * 1024) return 0;
+    if (d->in_scale != nullptr && d->cout == 256) return 0;
+    if (d->up_low != nullptr) {
+        // the TMA-fed upsample operand needs whole 2x2 blocks inside every 128-pixel tile
+        const int w = d->w, h = d->h;
+        const bool pow2 = (w & (w - 1)) == 0;
+        if (!pow2 || w > 64 || w < 2 || (h & 1)) return 0;
+        if (128 % (2 * w) != 0) return 0;
+    }
+    return 1;
+}
+
+int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
+    using namespace c1;
+    Params kp;
+    memset(&kp, 0, sizeof(kp));
+    const long long m = static_cast<long long>(d->n) * d->h * d->w;
+    if (m > 0x7fffffffLL) {
+        set_last_error("hg_conv_nhwc_bf16: too many pixels");
+        return HG_ERR_INVALID;
+    }
+    const bool prologue = d->in_scale != nullptr;
+    kp.bias = d->bias;
+    kp.in_scale = d->in_scale;
+    kp.in_shift = d->in_shift;
+    kp.err_word = d->err_word;
+    kp.num_tiles = static_cast<int>((m + kTileM - 1) / kTileM);
+    kp.kb1 = d->cin / 64;
+    kp.kb2 = d->cin2 / 64;
+    kp.cin = d->cin;
+    kp.has_res = d->residual != nullptr;
+    kp.has_up = d->up_low != nullptr ? d->w : 0;
+    kp.relu = d->relu;
+
+    // shared-memory budget -> pipeline depths
+    const int num_kb = kp.kb1 + kp.kb2;
+    const int wbytes = num_kb * d->cout * kBlockK * 2;
+    const int misc = d->cout * 4 + (prologue ? 2 * kMaxK * 4 : 0) + 512;     // bias, scale/shift, barriers
+    int avail = kSmemLimit - 1024 - wbytes - misc;
+    const int ring_unit = kSlabBytes + (kp.has_up ? kUpBytes : 0);
+    const int slabs = d->cout / 64;
+    // the staging ring wants >= one tile of slabs when it also prefetches a residual; the A ring gets the rest
+    int ring = kp.has_res ? (slabs < 2 ? 2 : (slabs < kMaxRing ? slabs : kMaxRing)) : 2;
+    int a_stages = (avail - ring * ring_unit) / kSlabBytes;
+    while (a_stages < 3 && ring > 2) {
+        --ring;
+        a_stages = (avail - ring * ring_unit) / kSlabBytes;
+    }
+    if (a_stages > kMaxAStages) a_stages = kMaxAStages;
+    if (a_stages < 2) {
+        set_last_error("conv1x1: shared-memory budget exhausted (K=%d N=%d)", d->cin + d->cin2, d->cout);
+        return HG_ERR_INVALID;
+    }
+    kp.a_stages = a_stages;
+    kp.ring = ring;
+    const int smem_bytes = 1024 + wbytes + a_stages * kSlabBytes + ring * ring_unit + misc;
+
+    int rc;
+    if ((rc = make_map(&kp.map_a, d->in, d->cin, m, kTileM)) != HG_OK) return rc;
+    if (d->in2 && (rc = make_map(&kp.map_a2, d->in2, d->cin2, m, kTileM)) != HG_OK) return rc;
+    if ((rc = make_map(&kp.map_b, d->weight, d->cin + d->cin2, d->cout, d->cout)) != HG_OK) return rc;
+    if ((rc = make_map(&kp.map_out, d->out, d->cout, m, kTileM)) != HG_OK) return rc;
+    if (d->residual && (rc = make_map(&kp.map_res, d->residual, d->cout, m, kTileM)) != HG_OK) return rc;
+    if (d->up_low && (rc = make_map(&kp.map_up, d->up_low, d->cout, m / 4, kUpRows)) != HG_OK) return rc;
+
+    switch (d->cout) {
+        case 64: return prologue ? launch<64, true>(kp, smem_bytes, stream) : launch<64, false>(kp, smem_bytes, stream);
+        case 128: return prologue ? launch<128, true>(kp, smem_bytes, stream) : launch<128, false>(kp, smem_bytes, stream);
+        case 256: return launch<256, false>(kp, smem_bytes, stream);
+    }
+    set_last_error("conv1x1: unsupported cout %d", d->cout);
+    return HG_ERR_INVALID;
+}
+
+}  // namespace hg

@@ -24,7 +24,13 @@
 #include <cstring>
 #include <mutex>
 
+#include <cstdlib>
+
 namespace hg {
+
+// second-generation flat 1x1 kernel (hg_conv1x1.cu)
+int conv1x1_supported(const hg_conv_desc* d);
+int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream);
 
 constexpr int kTileM = 128;          // pixels per tile (UMMA M)
 constexpr int kBlockK = 64;          // bf16 elements per k-block = one 128-byte swizzle row
@@ -531,6 +537,12 @@ extern "C" int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream_v) {
     if (d->up_low && ((d->h & 1) || (d->w & 1))) {
         set_last_error("hg_conv_nhwc_bf16: up_low needs even h,w");
         return HG_ERR_INVALID;
+    }
+
+    {
+        // HG_CONV1X1_GENERIC=1 forces the generic kernel for 1x1 convs (A/B comparisons only)
+        static const bool force_generic = getenv("HG_CONV1X1_GENERIC") != nullptr;
+        if (!force_generic && conv1x1_supported(d)) return conv1x1_launch(d, stream);
     }
 
     ConvKernelParams kp;

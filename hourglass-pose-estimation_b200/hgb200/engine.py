@@ -51,10 +51,12 @@ class Plan:
     def __init__(self, device):
         self.device = device
         self.launches: List[Callable[[], None]] = []
+        self.meta: List[dict] = []          # one entry per launch: op class, algorithmic flops / bytes
         self.input: Optional[torch.Tensor] = None
         self.outputs: List[torch.Tensor] = []
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.arena_bytes = 0
+        self.heatmap = self.center = self.scale = self.coords = None
 
     @property
     def num_launches(self) -> int:
@@ -77,6 +79,22 @@ class Plan:
         with torch.cuda.graph(g):
             self.run_eager()
         self.graph = g
+
+    def profile(self, iters: int = 1):
+        """Eager replay with a CUDA-event pair around every launch (on the launching stream).
+        Returns per-launch milliseconds averaged over `iters` -- used for the roofline figures."""
+        st = torch.cuda.current_stream(self.device)
+        total = [0.0] * len(self.launches)
+        for _ in range(iters):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.launches) + 1)]
+            evs[0].record(st)
+            for i, fn in enumerate(self.launches):
+                fn()
+                evs[i + 1].record(st)
+            torch.cuda.synchronize(self.device)
+            for i in range(len(self.launches)):
+                total[i] += evs[i].elapsed_time(evs[i + 1])
+        return [t / iters for t in total]
 
     def run(self):
         if self.graph is not None:
@@ -121,7 +139,13 @@ class HourglassEngine:
         return out
 
     # ------------------------------------------------------------------ plan construction
-    def build_plan(self, n: int, h: int, w: int, flip: bool = False, use_graph: bool = True) -> Plan:
+    def build_plan(self, n: int, h: int, w: int, flip=False, use_graph: bool = True, last_only: bool = False,
+                   decode: Optional[dict] = None) -> Plan:
+        """flip: False | True (mirrored input) | 'both' (flip test: the batch is doubled internally --
+        images [0,n) as given, [n,2n) mirrored -- so the small pyramid levels see twice the rows).
+        last_only: emit only the last stack's heat map (inference; the remap GEMM does not need the
+        intermediate heat maps).  decode: {'flip_pairs': [...], 'output_size': (w,h)} appends the
+        flip-average + get_final_preds_v1 kernels; results in plan.heatmap / plan.coords."""
         if h % 64 or w % 64:
             raise HgError(f"input {h}x{w}: height and width must be multiples of 64 (4 pooling levels on H/4 x W/4)")
         dev = self.device
@@ -130,10 +154,24 @@ class HourglassEngine:
         arena = _Arena(dev)
         L = plan.launches
         plan.input = torch.zeros((n, 3, h, w), dtype=torch.float32, device=dev)
+        both = (flip == 'both')
+        nb = 2 * n if both else n           # rows the network sees
 
         def conv(x, wt, bias, *, ksize, cout, relu=False, in_scale=None, in_shift=None, residual=None, up_low=None,
                  x2=None, out_f32=None):
             shape = x.shape[:3]
+            pixels = shape[0] * shape[1] * shape[2]
+            cin_, cin2_ = x.shape[3], (x2.shape[3] if x2 is not None else 0)
+            ktot = ksize * ksize * cin_ + cin2_
+            act_bytes = pixels * (cin_ + cin2_) * 2 + pixels * cout * (4 if out_f32 is not None else 2)
+            if residual is not None:
+                act_bytes += pixels * cout * 2
+            if up_low is not None:
+                act_bytes += pixels * cout * 2 // 4
+            plan.meta.append(dict(op=f"conv{ksize}x{ksize}_k{ktot}_n{cout}_{shape[1]}x{shape[2]}"
+                                     + ("_pro" if in_scale is not None else "") + ("_res" if residual is not None else "")
+                                     + ("_up" if up_low is not None else ""),
+                                  kind="conv", flops=2.0 * pixels * ktot * cout, bytes=act_bytes + wt.numel() * 2))
             if out_f32 is not None:
                 L.append(lambda: ops.conv_nhwc(x, wt, bias, ksize=ksize, cout=cout, relu=relu, heads=True,
                                                out_nchw_f32=out_f32))
@@ -167,6 +205,7 @@ class HourglassEngine:
         def pool(x):
             nb, hh, ww, c = x.shape
             out = arena.get((nb, hh // 2, ww // 2, c))
+            plan.meta.append(dict(op=f"maxpool_{hh}x{ww}_c{c}", kind="bw", flops=0.0, bytes=x.numel() * 2 * 1.25))
             L.append(lambda: ops.maxpool2x2(x, out))
             return out
 
@@ -185,9 +224,17 @@ class HourglassEngine:
             return out
 
         # ---- stem
-        rows = arena.get((n, h // 2, w // 2, 192))
+        rows = arena.get((nb, h // 2, w // 2, 192))
         x_in = plan.input
-        L.append(lambda: ops.stem_im2col(x_in, flip_w=flip, out=rows))
+        im2col_bytes = n * 3 * h * w * 4 + n * (h // 2) * (w // 2) * 192 * 2
+        if both:
+            r0, r1 = rows[:n], rows[n:]
+            L.append(lambda: ops.stem_im2col(x_in, flip_w=False, out=r0))
+            L.append(lambda: ops.stem_im2col(x_in, flip_w=True, out=r1))
+            plan.meta += [dict(op="stem_im2col", kind="bw", flops=0.0, bytes=im2col_bytes)] * 2
+        else:
+            L.append(lambda: ops.stem_im2col(x_in, flip_w=bool(flip), out=rows))
+            plan.meta.append(dict(op="stem_im2col", kind="bw", flops=0.0, bytes=im2col_bytes))
         s0 = conv(rows, W.stem_w, W.stem_b, ksize=1, cout=64, relu=True)
         arena.put(rows)
         l1 = chain(W.layer1, s0, keep_input=False)
@@ -203,16 +250,34 @@ class HourglassEngine:
             fw, fb = W.fc[i]
             y2 = conv(y, fw, fb, ksize=1, cout=256, relu=True)
             arena.put(y)
-            out_i = torch.empty((n, self.num_classes, hm_h, hm_w), dtype=torch.float32, device=dev)
-            sw, sb = W.score[i]
-            conv(y2, sw, sb, ksize=1, cout=self.num_classes, out_f32=out_i)
-            plan.outputs.append(out_i)
+            if not last_only or i == self.num_stacks - 1:
+                out_i = torch.empty((nb, self.num_classes, hm_h, hm_w), dtype=torch.float32, device=dev)
+                sw, sb = W.score[i]
+                conv(y2, sw, sb, ksize=1, cout=self.num_classes, out_f32=out_i)
+                plan.outputs.append(out_i)
             if i < self.num_stacks - 1:
                 mw, mb = W.remap[i]
                 x_next = conv(y2, mw, mb, ksize=1, cout=256, residual=x)
                 arena.put(x)
                 x = x_next
             arena.put(y2)
+        if decode is not None:
+            hm = plan.outputs[-1]
+            if both:
+                from .flip import flip_perm_tensor
+                perm = flip_perm_tensor(self.num_classes, decode.get('flip_pairs') or [], dev)
+                avg = torch.empty((n, self.num_classes, hm_h, hm_w), dtype=torch.float32, device=dev)
+                h0, h1 = hm[:n], hm[n:]
+                L.append(lambda: ops.flip_average(h0, h1, perm, out=avg))
+                plan.meta.append(dict(op="flip_average", kind="bw", flops=0.0, bytes=avg.numel() * 4 * 3))
+                hm = avg
+            plan.heatmap = hm
+            plan.center = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+            plan.scale = torch.ones((n, 2), dtype=torch.float64, device=dev)
+            plan.coords = torch.empty((n, self.num_classes, 2), dtype=torch.float64, device=dev)
+            osz = decode.get('output_size') or (hm_w, hm_h)
+            L.append(lambda: ops.decode_final_preds_into(hm, plan.center, plan.scale, plan.coords, osz))
+            plan.meta.append(dict(op="decode_final_preds", kind="bw", flops=0.0, bytes=hm.numel() * 4))
         plan.arena_bytes = arena.total_bytes
         if use_graph:
             plan.capture()

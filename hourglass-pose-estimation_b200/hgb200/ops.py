@@ -186,9 +186,19 @@ def decode_final_preds(hm: torch.Tensor, center, scale, output_size) -> torch.Te
     return out
 
 
+def decode_final_preds_into(hm, center, scale, out, output_size):
+    """Pointer-stable form for static plans: every argument is a preallocated device tensor."""
+    _require_cuda(hm, center, scale, out)
+    b, j, h, w = hm.shape
+    lib.check(lib.hg_decode_final_preds(_ptr(hm), _ptr(center), _ptr(scale), _ptr(out), b, j, h, w, int(output_size[0]),
+                                        int(output_size[1]), _stream()), "hg_decode_final_preds")
+    return out
+
+
 def flip_average(hm: torch.Tensor, hm_flip: torch.Tensor, perm: torch.Tensor, out: Optional[torch.Tensor] = None):
-    hm, hm_flip = _hm(hm), _hm(hm_flip)
-    _require_cuda(perm)
+    if out is None:
+        hm, hm_flip = _hm(hm), _hm(hm_flip)
+    _require_cuda(hm, hm_flip, perm, out)
     b, j, h, w = hm.shape
     if out is None:
         out = torch.empty_like(hm)

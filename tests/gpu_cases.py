@@ -44,6 +44,16 @@ CONV_CASES = [
     ("heads_j17", 2, 64, 48, 256, 17, 1, False, False, False, False, 0, True),
     ("heads_j21", 1, 16, 16, 256, 21, 1, False, False, False, False, 0, True),
     ("heads_j14", 3, 8, 8, 256, 14, 1, False, False, False, False, 0, True),
+    ("1x1_up_32x32", 3, 32, 32, 128, 256, 1, False, False, True, True, 0, False),
+    ("1x1_up_8x8", 6, 8, 8, 128, 256, 1, False, False, True, True, 0, False),
+    ("1x1_up_8x8_odd_n", 5, 8, 8, 128, 256, 1, False, False, True, True, 0, False),
+    ("1x1_up_4x4", 9, 4, 4, 128, 256, 1, False, False, True, True, 0, False),
+    ("1x1_up_64x48_generic", 2, 64, 48, 128, 256, 1, False, False, True, True, 0, False),
+    ("1x1_up_6x6_generic", 3, 6, 6, 128, 256, 1, False, False, True, True, 0, False),
+    ("1x1_ragged_res_n256", 3, 10, 6, 128, 256, 1, False, False, True, False, 0, False),
+    ("1x1_two_inputs_n256", 2, 32, 32, 128, 256, 1, False, False, False, False, 128, False),
+    ("1x1_remap_relu", 2, 64, 64, 256, 256, 1, True, False, True, False, 0, False),
+    ("1x1_k192_n64_stem", 1, 128, 128, 192, 64, 1, True, False, False, False, 0, False),
     ("1x1_many_tiles", 8, 64, 64, 256, 128, 1, True, True, False, False, 0, False),
     ("3x3_many_tiles", 6, 64, 64, 128, 128, 3, True, False, False, False, 0, False),
     ("1x1_n256_many_tiles", 6, 64, 64, 128, 256, 1, False, False, True, True, 0, False),
