@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -22,6 +23,11 @@ int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return HG_OK;
     set_last_error("CUDA error %d (%s) at: %s", (int)e, cudaGetErrorString(e), what);
     return HG_ERR_CUDA;
+}
+
+bool pdl_enabled() {
+    static const bool on = getenv("HG_NO_PDL") == nullptr;
+    return on;
 }
 
 int num_sms() {

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <utility>
 
 namespace hg {
 
@@ -22,6 +23,26 @@ int check_cuda(cudaError_t e, const char* what);   // returns 0 or HG_ERR_CUDA a
     } while (0)
 
 int num_sms();   // SM count of the current device (cached per device)
+bool pdl_enabled();   // programmatic dependent launch on (default) unless HG_NO_PDL is set
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may start while its
+// predecessor in the stream drains; it must execute pdl_wait() before touching anything the
+// predecessor wrote (or still reads).  Falls back to a plain launch when PDL is disabled.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 
 
@@ -40,6 +61,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
     return r;
 }
+
+// programmatic dependent launch (no-ops when the kernel was launched without the attribute)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier

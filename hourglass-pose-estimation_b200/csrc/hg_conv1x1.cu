@@ -121,12 +121,15 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_launch_dependents();     // the next kernel in the stream may begin its own setup
 
     if (warp_idx == 0) {
         // ===================== A producer: resident weights once, then the A slab stream =====================
         if (lane == 0) {
+            // weights / bias / bn vectors are constants: fetched BEFORE waiting on the predecessor kernel
             mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(num_kb * kBStage));
             for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem_w + kb * kBStage, &p.map_b, w_bar, kb * kBlockK, 0);
+            pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
     } else if (warp_idx == 2) {
         // ===================== staging-ring producer: residual / upsample operands by TMA =====================
         if (lane == 0) {
+            pdl_wait();
             int buf = 0;
             uint32_t phase = 0;
             bool ok = true;
@@ -210,6 +214,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
         }
     } else if (warp_idx >= 4 && warp_idx < 8) {
         // ===================== epilogue =====================
+        pdl_wait();
         const int q = warp_idx & 3;
         const int row = q * 32 + lane;
         const bool leader = (warp_idx == 4 && lane == 0);
@@ -424,8 +429,7 @@ static int launch(const Params& kp, int smem_bytes, cudaStream_t stream) {
         }
     }
     const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
-    kern<<<grid, kPrologue ? 384 : 256, smem_bytes, stream>>>(kp);
-    HG_CUDA_OK(cudaGetLastError());
+    HG_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kPrologue ? 384 : 256), smem_bytes, stream, kp));
     return HG_OK;
 }
 

@@ -138,6 +138,8 @@ conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_launch_dependents();
+    pdl_wait();      // everything below reads or overwrites tensors the predecessor kernel may still touch
 
     // ------------------------------------------------------------------ roles
     if (warp_idx == 0) {
@@ -490,8 +492,7 @@ static int launch_conv(const ConvKernelParams& kp, cudaStream_t stream) {
         }
     }
     const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(kp);
-    HG_CUDA_OK(cudaGetLastError());
+    HG_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, kp));
     return HG_OK;
 }
 

@@ -26,6 +26,8 @@ __device__ __forceinline__ uint32_t bf16x2_add_f32(uint32_t a, uint32_t b) {   /
 // ---------------------------------------------------------------- max pool 2x2 stride 2
 __global__ void __launch_bounds__(kEwThreads) maxpool2x2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out,
                                                                  int n, int h, int w, int c8) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int oh = h >> 1, ow = w >> 1;
     const long long total = static_cast<long long>(n) * oh * ow * c8;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -54,6 +56,8 @@ __global__ void __launch_bounds__(kEwThreads) maxpool2x2_kernel(const uint4* __r
 __global__ void __launch_bounds__(kEwThreads) upsample_add_kernel(const uint4* __restrict__ a,
                                                                    const uint4* __restrict__ low,
                                                                    uint4* __restrict__ out, int n, int h, int w, int c8) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = static_cast<long long>(n) * h * w * c8;
     const int lh = h >> 1, lw = w >> 1;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -80,6 +84,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_kernel(const uint4* __rest
                                                               const float* __restrict__ scale,
                                                               const float* __restrict__ shift, uint4* __restrict__ out,
                                                               long long pixels, int c8) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long total = pixels * c8;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -103,6 +109,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_relu_kernel(const uint4* __rest
 constexpr int kStemK = 192;
 __global__ void __launch_bounds__(kEwThreads) stem_im2col_kernel(const float* __restrict__ in, uint4* __restrict__ out,
                                                                   int n, int h, int w, int flip_w) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int oh = h >> 1, ow = w >> 1;
     const long long total = static_cast<long long>(n) * oh * ow * (kStemK / 8);
     const long long plane = static_cast<long long>(h) * w;
@@ -180,9 +188,8 @@ extern "C" int hg_maxpool2x2_nhwc(const void* in, void* out, int32_t n, int32_t 
         return HG_ERR_INVALID;
     }
     const long long items = static_cast<long long>(n) * (h / 2) * (w / 2) * (c / 8);
-    maxpool2x2_kernel<<<ew_grid(items), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4*>(in), static_cast<uint4*>(out), n, h, w, c / 8);
-    HG_CUDA_OK(cudaGetLastError());
+    HG_CUDA_OK(launch_kernel(maxpool2x2_kernel, dim3(ew_grid(items)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(stream),
+                             static_cast<const uint4*>(in), static_cast<uint4*>(out), n, h, w, c / 8));
     return HG_OK;
 }
 
@@ -220,9 +227,8 @@ extern "C" int hg_stem_im2col(const float* in_nchw, void* out_rows, int32_t n, i
         return HG_ERR_INVALID;
     }
     const long long items = static_cast<long long>(n) * (h / 2) * (w / 2) * (kStemK / 8);
-    stem_im2col_kernel<<<ew_grid(items), kEwThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        in_nchw, static_cast<uint4*>(out_rows), n, h, w, flip_w);
-    HG_CUDA_OK(cudaGetLastError());
+    HG_CUDA_OK(launch_kernel(stem_im2col_kernel, dim3(ew_grid(items)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(stream),
+                             in_nchw, static_cast<uint4*>(out_rows), n, h, w, flip_w));
     return HG_OK;
 }
 
