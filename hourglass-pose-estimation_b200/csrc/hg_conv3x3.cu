@@ -1,0 +1,353 @@
+// 3x3 convolution (stride 1, pad 1) as implicit GEMM on tcgen05, second generation.
+//
+// The first-generation kernel (hg_conv_gemm.cu) fetches every filter tap as its own TMA box: nine
+// L2 -> shared-memory reads of the same pixels per tile, which leaves it L2-bandwidth bound at ~37 % of
+// the tensor pipe.  This kernel reads each input pixel ONCE per tile:
+//
+//   * the input lives in a HALO-PADDED layout in HBM: [1 zero row][n][h+1][w+1][c] -- one zero column
+//     right of every image row and one zero row under every image (written by the producing 1x1
+//     kernel through a strided TMA store; the pads are zeroed once and never touched).  In the flat
+//     "position" index f every 3x3 tap is then a CONSTANT offset dy*(w+1)+dx, and the pads are the
+//     convolution's zero padding on all four sides.
+//   * a tile is 256 consecutive positions.  Its halo'd run (256 + 2(w+1) + 2 positions x 64 channels) is
+//     loaded once into 128-byte-swizzled shared memory; the A operand of tap (dy,dx) is the same
+//     buffer with the UMMA descriptor's start address shifted by whole 128-byte rows (the hardware
+//     swizzles on absolute address bits, so row-shifted descriptors are exact -- probed on B200).
+//   * two 128-row accumulators share every B k-block, halving weight traffic again.
+//
+// Per 256 outputs: A traffic 2 x 50 KiB (was 2 x 288 KiB), B traffic 288 KiB (was 576 KiB).
+// Warp roles: 0 = A producer, 1 = MMA issuer + TMEM owner, 2 = B producer, 4..7 = epilogue.
+#include "hg_common.cuh"
+#include "../../include/hg_api.h"
+
+#include <cudaTypedefs.h>
+#include <cstring>
+#include <mutex>
+
+namespace hg {
+namespace c3 {
+
+constexpr int kBM = 256;            // positions per tile (two UMMA M=128 sub-tiles)
+constexpr int kBlockK = 64;
+constexpr int kMaxBStages = 8;
+constexpr int kSmemLimit = 232448;
+
+struct Params {
+    CUtensorMap map_a;      // (c, positions) over the halo-padded input
+    CUtensorMap map_b;      // (k, cout) weights, k = tap*cin + c
+    const float* bias;
+    __nv_bfloat16* out;     // dense NHWC [n][h][w][cout]
+    unsigned int* err_word;
+    int H, W, P, NB;
+    int cin, cout, slabs;
+    int num_tiles;
+    long long total_pos;    // NB*(H+1)*P  (positions after the leading zero row)
+    int box_rows, num_boxes, region_bytes;   // halo'd run = num_boxes TMA boxes of box_rows rows
+    int b_stages;
+    int relu;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__ Params p) {
+    constexpr int kBStage = BLOCK_N * kBlockK * 2;
+    constexpr int kTmemCols = 4 * BLOCK_N;            // 2 accumulator stages x 2 sub-tiles
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                    // 2 regions
+    uint8_t* smem_b = smem_a + 2 * p.region_bytes;             // b_stages x kBStage
+    float* s_bias = reinterpret_cast<float*>(smem_b + p.b_stages * kBStage);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
+    uint64_t* a_full = bars;                  // [2]
+    uint64_t* a_empty = bars + 2;             // [2]
+    uint64_t* b_full = bars + 4;              // [kMaxBStages]
+    uint64_t* b_empty = b_full + kMaxBStages;
+    uint64_t* tmem_full_bar = b_empty + kMaxBStages;   // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&p.map_a);
+        tma_prefetch_desc(&p.map_b);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+            mbar_init(&tmem_full_bar[s], 1);
+            mbar_init(&tmem_empty_bar[s], 4);
+        }
+        for (int s = 0; s < kMaxBStages; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp_idx == 1) tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_launch_dependents();
+
+    const int halo = p.P + 1;                 // positions before the tile start that the taps reach
+
+    if (warp_idx == 0) {
+        // ===================== A producer: one halo'd run per (tile, 64-channel slab) =====================
+        if (lane == 0) {
+            pdl_wait();
+            int it = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+                // position 0 of the tensor map is the leading zero row; tiles start after it
+                const long long f0 = static_cast<long long>(p.P) + static_cast<long long>(tile) * kBM;
+                const int row0 = static_cast<int>(f0 - halo);
+                for (int slab = 0; slab < p.slabs; ++slab, ++it) {
+                    const int buf = it & 1;
+                    ok = mbar_wait(&a_empty[buf], ((it >> 1) & 1u) ^ 1u, p.err_word, 0x3101);
+                    if (!ok) break;
+                    mbar_arrive_expect_tx(&a_full[buf], static_cast<uint32_t>(p.num_boxes * p.box_rows * 128));
+                    for (int b = 0; b < p.num_boxes; ++b)
+                        tma_load_2d(smem_a + buf * p.region_bytes + b * p.box_rows * 128, &p.map_a, &a_full[buf],
+                                    slab * kBlockK, row0 + b * p.box_rows);
+                }
+            }
+        }
+    } else if (warp_idx == 2) {
+        // ===================== B producer: weight k-blocks (tap, slab), streamed =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+                for (int slab = 0; slab < p.slabs && ok; ++slab) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ok = mbar_wait(&b_empty[stage], phase ^ 1u, p.err_word, 0x3301);
+                        if (!ok) break;
+                        mbar_arrive_expect_tx(&b_full[stage], kBStage);
+                        tma_load_2d(smem_b + stage * kBStage, &p.map_b, &b_full[stage], tap * p.cin + slab * kBlockK, 0);
+                        if (++stage == p.b_stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0, a_it = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                ok = mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1u) ^ 1u, p.err_word, 0x3201);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 2 * BLOCK_N);
+                for (int slab = 0; slab < p.slabs && ok; ++slab, ++a_it) {
+                    const int buf = a_it & 1;
+                    ok = mbar_wait(&a_full[buf], (a_it >> 1) & 1u, p.err_word, 0x3202);
+                    if (!ok) break;
+                    const uint32_t a_base = smem_u32(smem_a + buf * p.region_bytes);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ok = mbar_wait(&b_full[stage], phase, p.err_word, 0x3203);
+                        if (!ok) break;
+                        tc_fence_after();
+                        const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                        const uint32_t row_off = static_cast<uint32_t>(halo + dy * p.P + dx);   // >= 0 by construction
+                        const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + stage * kBStage));
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const uint64_t a_desc = umma_desc_sw128(a_base + (row_off + half * 128) * 128);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_bf16(d_tmem + half * BLOCK_N, a_desc + 2u * k, b_desc + 2u * k, idesc,
+                                            (slab | tap | k) != 0 ? 1u : 0u);
+                        }
+                        tc_commit(&b_empty[stage]);
+                        if (++stage == p.b_stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    if (ok) tc_commit(&a_empty[buf]);
+                }
+                if (ok) tc_commit(&tmem_full_bar[acc]);
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // ===================== epilogue: bias + ReLU -> bf16, dense NHWC stores (pads skipped) =====================
+        pdl_wait();
+        const int q = warp_idx & 3;
+        const int row = q * 32 + lane;
+        const long long img_pos = static_cast<long long>(p.H + 1) * p.P;
+        int it = 0;
+        bool ok = true;
+        for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            ok = mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1u, p.err_word, 0x3401);
+            if (!ok) break;
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const long long f = static_cast<long long>(tile) * kBM + half * 128 + row;     // position after the zero row
+                const long long n = f / img_pos;
+                const int r = static_cast<int>(f - n * img_pos);
+                const int y = r / p.P, x = r - y * p.P;
+                const bool valid = (f < p.total_pos) && (x < p.W) && (y < p.H);
+                __nv_bfloat16* o = p.out + ((n * p.H + y) * p.W + x) * p.cout;
+                const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                       static_cast<uint32_t>(acc * 2 * BLOCK_N + half * BLOCK_N);
+#pragma unroll
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_row + c0, v);
+                    tmem_ld_wait();
+                    if (half == 1 && c0 == BLOCK_N - 32) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float f8[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                f8[j] = __uint_as_float(v[i * 8 + j]) + s_bias[c0 + i * 8 + j];
+                                if (p.relu) f8[j] = fmaxf(f8[j], 0.f);
+                            }
+                            uint4 w4;
+                            w4.x = pack_bf16x2(f8[0], f8[1]);
+                            w4.y = pack_bf16x2(f8[2], f8[3]);
+                            w4.z = pack_bf16x2(f8[4], f8[5]);
+                            w4.w = pack_bf16x2(f8[6], f8[7]);
+                            *reinterpret_cast<uint4*>(o + c0 + i * 8) = w4;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static std::mutex mu;
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+            set_last_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+            return nullptr;
+        }
+        fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+    auto enc = encode_fn();
+    if (!enc) return HG_ERR_CUDA;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("conv3x3: cuTensorMapEncodeTiled failed: CUresult %d (cols %llu rows %llu box_rows %u)", (int)r,
+                       (unsigned long long)cols, (unsigned long long)rows, box_rows);
+        return HG_ERR_CUDA;
+    }
+    return HG_OK;
+}
+
+template <int BLOCK_N>
+static int launch(const Params& kp, int smem_bytes, cudaStream_t stream) {
+    auto kern = conv3x3_kernel<BLOCK_N>;
+    static std::mutex mu;
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    HG_CUDA_OK(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 64 || !(done_mask >> dev & 1ull)) {
+            HG_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            if (dev < 64) done_mask |= 1ull << dev;
+        }
+    }
+    const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+    HG_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(256), smem_bytes, stream, kp));
+    return HG_OK;
+}
+
+}  // namespace c3
+}  // namespace hg
+
+// Elements a halo-padded activation buffer needs: one leading zero row + n*(h+1)*(w+1) positions.
+extern "C" int64_t hg_halo_padded_elems(int32_t n, int32_t h, int32_t w, int32_t c) {
+    return (static_cast<int64_t>(n) * (h + 1) * (w + 1) + (w + 1)) * c;
+}
+
+extern "C" int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, const float* bias, void* out,
+                                    unsigned int* err_word, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                                    int32_t relu, void* stream) {
+    using namespace hg;
+    using namespace hg::c3;
+    if (!in_padded || !weight || !out || n <= 0 || h <= 0 || w <= 0 || cin % 64 != 0 || cin <= 0 ||
+        (cout != 64 && cout != 128) || w > 253) {
+        set_last_error("hg_conv3x3_halo_bf16: bad arguments (cin %% 64 == 0, cout in {64,128}, w <= 253)");
+        return HG_ERR_INVALID;
+    }
+    Params kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.bias = bias;
+    kp.out = static_cast<__nv_bfloat16*>(out);
+    kp.err_word = err_word;
+    kp.H = h;
+    kp.W = w;
+    kp.P = w + 1;
+    kp.NB = n;
+    kp.cin = cin;
+    kp.cout = cout;
+    kp.slabs = cin / 64;
+    kp.relu = relu;
+    kp.total_pos = static_cast<long long>(n) * (h + 1) * kp.P;
+    kp.num_tiles = static_cast<int>((kp.total_pos + kBM - 1) / kBM);
+    const int region_rows = kBM + 2 * kp.P + 2;
+    kp.num_boxes = (region_rows + 255) / 256;
+    kp.box_rows = ((region_rows + kp.num_boxes - 1) / kp.num_boxes + 7) / 8 * 8;
+    kp.region_bytes = kp.num_boxes * kp.box_rows * 128;
+    const int b_stage = cout * 128;
+    const int misc = cout * 4 + 512;
+    int b_stages = (kSmemLimit - 1024 - 2 * kp.region_bytes - misc) / b_stage;
+    if (b_stages > kMaxBStages) b_stages = kMaxBStages;
+    if (b_stages < 2) {
+        set_last_error("hg_conv3x3_halo_bf16: image too wide for the shared-memory budget (w=%d)", w);
+        return HG_ERR_INVALID;
+    }
+    kp.b_stages = b_stages;
+    const int smem_bytes = 1024 + 2 * kp.region_bytes + b_stages * b_stage + misc;
+    const uint64_t rows = static_cast<uint64_t>(kp.total_pos) + kp.P;       // incl. the leading zero row
+    int rc;
+    if ((rc = make_map(&kp.map_a, in_padded, cin, rows, kp.box_rows)) != HG_OK) return rc;
+    if ((rc = make_map(&kp.map_b, weight, 9ull * cin, cout, cout)) != HG_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return cout == 64 ? launch<64>(kp, smem_bytes, st) : launch<128>(kp, smem_bytes, st);
+}

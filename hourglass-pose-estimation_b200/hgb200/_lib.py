@@ -36,6 +36,8 @@ _SIGNATURES = {
     "hg_check_device": ([], C.c_int),
     "hg_conv_nhwc_bf16": ([C.POINTER(ConvDesc), _vp], C.c_int),
     "hg_stem_im2col": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_stem_pack": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_stem_conv": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp], C.c_int),
     "hg_maxpool2x2_nhwc": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_upsample2x_add_nhwc": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_bn_relu_nhwc": ([_vp, _vp, _vp, _vp, _i64, _i32, _vp], C.c_int),

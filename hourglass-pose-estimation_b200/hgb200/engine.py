@@ -223,20 +223,23 @@ class HourglassEngine:
             arena.put(low3)
             return out
 
-        # ---- stem
-        rows = arena.get((nb, h // 2, w // 2, 192))
+        # ---- stem: pack to NHWC4 (+mirror for the flip half) -> windowed implicit GEMM, no im2col matrix
         x_in = plan.input
-        im2col_bytes = n * 3 * h * w * 4 + n * (h // 2) * (w // 2) * 192 * 2
+        packed = ops.stem_packed_buffer(nb, h, w, dev)           # outside the arena: its zero padding must persist
+        plan.keep = [packed]
+        pack_bytes = n * 3 * h * w * 4 + n * h * w * 8
         if both:
-            r0, r1 = rows[:n], rows[n:]
-            L.append(lambda: ops.stem_im2col(x_in, flip_w=False, out=r0))
-            L.append(lambda: ops.stem_im2col(x_in, flip_w=True, out=r1))
-            plan.meta += [dict(op="stem_im2col", kind="bw", flops=0.0, bytes=im2col_bytes)] * 2
+            pk0, pk1 = packed[:n], packed[n:]
+            L.append(lambda a=pk0: ops.stem_pack(x_in, a, flip_w=False))
+            L.append(lambda a=pk1: ops.stem_pack(x_in, a, flip_w=True))
+            plan.meta += [dict(op="stem_pack", kind="bw", flops=0.0, bytes=pack_bytes)] * 2
         else:
-            L.append(lambda: ops.stem_im2col(x_in, flip_w=bool(flip), out=rows))
-            plan.meta.append(dict(op="stem_im2col", kind="bw", flops=0.0, bytes=im2col_bytes))
-        s0 = conv(rows, W.stem_w, W.stem_b, ksize=1, cout=64, relu=True)
-        arena.put(rows)
+            L.append(lambda a=packed: ops.stem_pack(x_in, a, flip_w=bool(flip)))
+            plan.meta.append(dict(op="stem_pack", kind="bw", flops=0.0, bytes=pack_bytes))
+        s0 = arena.get((nb, h // 2, w // 2, 64))
+        L.append(lambda a=packed, o=s0: ops.stem_conv(a, W.stem_w_win, W.stem_b, out=o))
+        plan.meta.append(dict(op=f"stem_conv7x7s2_{h}x{w}", kind="conv", flops=2.0 * nb * (h // 2) * (w // 2) * 147 * 64,
+                              bytes=nb * h * w * 8 + nb * (h // 2) * (w // 2) * 128))
         l1 = chain(W.layer1, s0, keep_input=False)
         p1 = pool(l1)
         arena.put(l1)

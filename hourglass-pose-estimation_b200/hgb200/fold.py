@@ -47,6 +47,16 @@ def gemm_weight(w4: torch.Tensor, extra: Optional[torch.Tensor] = None, k_pad: i
     return out.to(torch.bfloat16).contiguous()
 
 
+def stem_window_weight(w4: torch.Tensor):
+    """[64, 3, 7, 7] (fp32, BN already folded) -> bf16 [64, 224] for hg_stem_conv: k = ky*32 + (1+kx)*4 + c.
+    The A operand of filter row ky is the 8-pixel x 4-channel window starting one pixel left of the
+    first tap, so slots (pixel 0) and (channel 3) carry zero weights."""
+    cout = w4.shape[0]
+    m = w4.new_zeros(cout, 7, 8, 4)
+    m[:, :, 1:8, 0:3] = w4.permute(0, 2, 3, 1)          # [cout, ky, kx, c]
+    return m.reshape(cout, 224).to(torch.bfloat16).contiguous()
+
+
 def pad_bias(b: torch.Tensor):
     cout = b.shape[0]
     cout_pad = (cout + 15) // 16 * 16
@@ -105,7 +115,8 @@ class NetWeights:
             self.num_stacks += 1
         self.num_classes = sd["score.0.weight"].shape[0]
         w, b = fold_bn_after_conv(sd, "conv1", "bn1")
-        self.stem_w, self.stem_b = gemm_weight(w, k_pad=192), pad_bias(b)
+        self.stem_w, self.stem_b = gemm_weight(w, k_pad=192), pad_bias(b)     # im2col form (fallback / tests)
+        self.stem_w_win = stem_window_weight(w)                                # window form (hg_stem_conv)
         self.layer1 = chain_weights(sd, "layer1")
         self.layer2 = chain_weights(sd, "layer2")
         self.layer3 = chain_weights(sd, "layer3")

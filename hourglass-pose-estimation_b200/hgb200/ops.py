@@ -107,6 +107,34 @@ def stem_im2col(x_nchw: torch.Tensor, flip_w: bool = False, out: Optional[torch.
     return out
 
 
+def stem_packed_buffer(n: int, h: int, w: int, device) -> torch.Tensor:
+    """Zero-initialised NHWC4 bf16 staging image with 4 px of horizontal padding on both sides."""
+    return torch.zeros((n, h, w + 8, 4), dtype=torch.bfloat16, device=device)
+
+
+def stem_pack(x_nchw: torch.Tensor, packed: torch.Tensor, flip_w: bool = False) -> torch.Tensor:
+    _require_cuda(x_nchw, packed)
+    n, c, h, w = x_nchw.shape
+    if c != 3 or x_nchw.dtype != torch.float32 or tuple(packed.shape) != (n, h, w + 8, 4) or packed.dtype != torch.bfloat16:
+        raise HgError("stem_pack: expects fp32 [n,3,h,w] and a bf16 [n,h,w+8,4] buffer")
+    lib.check(lib.hg_stem_pack(_ptr(x_nchw), _ptr(packed), n, h, w, int(flip_w), _stream()), "hg_stem_pack")
+    return packed
+
+
+def stem_conv(packed: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None):
+    """packed [n,h,w+8,4] bf16 -> relu(conv7x7/s2 + bias): bf16 NHWC [n,h/2,w/2,64]."""
+    _require_cuda(packed, weight, bias, out)
+    n, h, wp, _ = packed.shape
+    w = wp - 8
+    if tuple(weight.shape) != (64, 224) or weight.dtype != torch.bfloat16 or bias.numel() < 64:
+        raise HgError("stem_conv: weight must be bf16 [64,224], bias fp32 [64]")
+    if out is None:
+        out = torch.empty((n, h // 2, w // 2, 64), dtype=torch.bfloat16, device=packed.device)
+    lib.check(lib.hg_stem_conv(_ptr(packed), _ptr(weight), _ptr(bias), _ptr(out), _ptr(err_word(packed.device)), n, h, w,
+                               _stream()), "hg_stem_conv")
+    return out
+
+
 def maxpool2x2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _require_cuda(x, out)
     n, h, w, c = x.shape

@@ -71,6 +71,31 @@ def test_stem_im2col_and_gemm(ops, dev):
         assert err <= float(ref.abs().max()) * 2 ** -7
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 96), (1, 256, 256), (2, 256, 192), (3, 128, 512)])
+def test_stem_window_conv(shape, ops, dev):
+    """7x7/s2 stem through the overlapping-window TMA path (no im2col matrix)."""
+    from hgb200.fold import stem_window_weight
+    no_tf32()
+    n, h, w = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(n, 3, h, w, generator=g)
+    wt = torch.randn(64, 3, 7, 7, generator=g) / 12.0
+    bias = torch.randn(64, generator=g) * 0.1
+    wwin = stem_window_weight(wt).to(dev)
+    for flip in (False, True):
+        packed = ops.stem_packed_buffer(n, h, w, dev)
+        ops.stem_pack(x.to(dev), packed, flip_w=flip)
+        xin = x.flip(-1) if flip else x
+        assert torch.equal(packed[:, :, 4:-4, :3], xin.permute(0, 2, 3, 1).to(torch.bfloat16).to(dev))
+        assert float(packed[:, :, :4].abs().max()) == 0 and float(packed[:, :, -4:].abs().max()) == 0
+        out = ops.stem_conv(packed, wwin, bias.to(dev))
+        torch.cuda.synchronize()
+        ops.check_err_word(dev)
+        ref = F.relu(F.conv2d(r16(xin).to(dev), r16(wt).to(dev), bias.to(dev), stride=2, padding=3))
+        err = float((out.float().permute(0, 3, 1, 2) - ref).abs().max())
+        assert err <= float(ref.abs().max()) * 2 ** -7, f"err {err}"
+
+
 # ------------------------------------------------------------------------------------------ bandwidth kernels
 @pytest.mark.parametrize("shape", [(2, 64, 64, 256), (3, 8, 8, 128), (1, 4, 6, 64), (5, 2, 2, 256)])
 def test_maxpool_bit_exact(shape, ops, dev):
