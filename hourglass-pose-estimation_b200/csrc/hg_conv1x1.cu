@@ -49,6 +49,7 @@ struct Params {
     int cin;
     int a_stages, ring;     // pipeline depths chosen by the host from the smem budget
     int has_res, has_up, relu;
+    int out_halo, img_h, img_w;     // out_halo: map_out is the 4-D strided view (c, x, y, n) of a halo-padded buffer
 };
 
 enum : uint32_t { kErrProducer = 0x1100, kErrMma = 0x1200, kErrRing = 0x1300, kErrEpilogue = 0x1400, kErrPrologue = 0x1500 };
@@ -309,7 +310,14 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                 fence_proxy_async_smem();
                 named_bar_sync(1, 128);
                 if (leader) {
-                    tma_store_2d(&p.map_out, smem_ring + buf * kSlabBytes, slab * 64, m0);
+                    if (p.out_halo) {
+                        const int hw = p.img_h * p.img_w;
+                        const int n_img = m0 / hw;
+                        const int y0 = (m0 - n_img * hw) / p.img_w;
+                        tma_store_4d(&p.map_out, smem_ring + buf * kSlabBytes, slab * 64, 0, y0, n_img);
+                    } else {
+                        tma_store_2d(&p.map_out, smem_ring + buf * kSlabBytes, slab * 64, m0);
+                    }
                     tma_store_commit();
                     if (prev_buf >= 0) {
                         tma_store_wait_read<1>();               // the previous slab's store has drained its smem
@@ -442,6 +450,9 @@ int conv1x1_supported(const hg_conv_desc* d) {
     const int k = d->cin + d->cin2;
     if (k > c1::kMaxK || static_cast<long long>(k) * d->cout * 2 > 128 * 1024) return 0;
     if (d->in_scale != nullptr && d->cout == 256) return 0;
+    if (d->out_halo) {
+        if (d->w > 128 || 128 % d->w != 0 || (static_cast<long long>(d->h) * d->w) % 128 != 0) return 0;
+    }
     if (d->up_low != nullptr) {
         // the TMA-fed upsample operand needs whole 2x2 blocks inside every 128-pixel tile
         const int w = d->w, h = d->h;
@@ -501,7 +512,29 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
     if ((rc = make_map(&kp.map_a, d->in, d->cin, m, kTileM)) != HG_OK) return rc;
     if (d->in2 && (rc = make_map(&kp.map_a2, d->in2, d->cin2, m, kTileM)) != HG_OK) return rc;
     if ((rc = make_map(&kp.map_b, d->weight, d->cin + d->cin2, d->cout, d->cout)) != HG_OK) return rc;
-    if ((rc = make_map(&kp.map_out, d->out, d->cout, m, kTileM)) != HG_OK) return rc;
+    kp.out_halo = d->out_halo;
+    kp.img_h = d->h;
+    kp.img_w = d->w;
+    if (d->out_halo) {
+        // strided 4-D view of the interior of [zero row][n][h+1][w+1][c]
+        auto enc = encode_fn();
+        if (!enc) return HG_ERR_CUDA;
+        const uint64_t C = d->cout, P = d->w + 1;
+        cuuint64_t gdim[4] = {C, static_cast<cuuint64_t>(d->w), static_cast<cuuint64_t>(d->h), static_cast<cuuint64_t>(d->n)};
+        cuuint64_t gstr[3] = {C * 2, P * C * 2, static_cast<cuuint64_t>(d->h + 1) * P * C * 2};
+        cuuint32_t box[4] = {64, static_cast<cuuint32_t>(d->w), static_cast<cuuint32_t>(kTileM / d->w), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        void* base = static_cast<char*>(d->out) + P * C * 2;        // skip the leading zero row
+        CUresult r = enc(&kp.map_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_last_error("conv1x1: halo-padded output tensor map failed: CUresult %d", (int)r);
+            return HG_ERR_CUDA;
+        }
+    } else if ((rc = make_map(&kp.map_out, d->out, d->cout, m, kTileM)) != HG_OK) {
+        return rc;
+    }
     if (d->residual && (rc = make_map(&kp.map_res, d->residual, d->cout, m, kTileM)) != HG_OK) return rc;
     if (d->up_low && (rc = make_map(&kp.map_up, d->up_low, d->cout, m / 4, kUpRows)) != HG_OK) return rc;
 

@@ -546,6 +546,11 @@ extern "C" int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream_v) {
         if (!force_generic && conv1x1_supported(d)) return conv1x1_launch(d, stream);
     }
 
+    if (d->out_halo) {
+        set_last_error("hg_conv_nhwc_bf16: out_halo needs a 1x1 conv with 128 %% w == 0, (h*w) %% 128 == 0, cout in {64,128,256}");
+        return HG_ERR_INVALID;
+    }
+
     ConvKernelParams kp;
     memset(&kp, 0, sizeof(kp));
     kp.bias = d->bias;

@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p), ("out_nchw_f32", C.c_void_p), ("err_word", C.c_void_p),
         ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
         ("cin", C.c_int32), ("cin2", C.c_int32), ("cout", C.c_int32),
-        ("ksize", C.c_int32), ("relu", C.c_int32),
+        ("ksize", C.c_int32), ("relu", C.c_int32), ("out_halo", C.c_int32),
     ]
 
 
@@ -36,6 +36,8 @@ _SIGNATURES = {
     "hg_check_device": ([], C.c_int),
     "hg_conv_nhwc_bf16": ([C.POINTER(ConvDesc), _vp], C.c_int),
     "hg_stem_im2col": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_halo_padded_elems": ([_i32, _i32, _i32, _i32], C.c_int64),
+    "hg_conv3x3_halo_bf16": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_stem_pack": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_stem_conv": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp], C.c_int),
     "hg_maxpool2x2_nhwc": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),

@@ -17,6 +17,7 @@ Dataflow (reference: src/models/hourglass.py:69-90, src/models/modules.py:27-47,
 """
 from __future__ import annotations
 
+import os
 from collections import defaultdict
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -43,6 +44,19 @@ class _Arena:
 
     def put(self, t: torch.Tensor):
         self.free[(tuple(t.shape), t.dtype)].append(t)
+
+    # halo-padded activations ([zero row][n][h+1][w+1][c], see hg_conv3x3_halo_bf16): zeroed once at
+    # allocation; producers only write the interior, so a recycled buffer's pads are still zero.
+    def get_halo(self, n, h, w, c) -> torch.Tensor:
+        key = ("halo", n, h, w, c)
+        if self.free[key]:
+            return self.free[key].pop()
+        t = ops.halo_padded_buffer(n, h, w, c, self.device)
+        self.total_bytes += t.numel() * t.element_size()
+        return t
+
+    def put_halo(self, t: torch.Tensor, n, h, w, c):
+        self.free[("halo", n, h, w, c)].append(t)
 
 
 class Plan:
@@ -156,6 +170,7 @@ class HourglassEngine:
         plan.input = torch.zeros((n, 3, h, w), dtype=torch.float32, device=dev)
         both = (flip == 'both')
         nb = 2 * n if both else n           # rows the network sees
+        halo_min_w = int(os.environ.get("HG_HALO_MIN_W", "32"))   # levels at least this wide use the halo 3x3 kernel
 
         def conv(x, wt, bias, *, ksize, cout, relu=False, in_scale=None, in_shift=None, residual=None, up_low=None,
                  x2=None, out_f32=None):
@@ -182,9 +197,28 @@ class HourglassEngine:
             return out
 
         def block(bw: BlockWeights, x, up_low=None):
-            a2 = conv(x, bw.w1, bw.b1, ksize=1, cout=bw.planes, relu=True, in_scale=bw.s1, in_shift=bw.t1)
-            a3 = conv(a2, bw.w2, bw.b2, ksize=3, cout=bw.planes, relu=True)
-            arena.put(a2)
+            bn_, bh_, bw_, _ = x.shape
+            if (bw_ >= halo_min_w and bw_ <= 128 and 128 % bw_ == 0 and (bh_ * bw_) % 128 == 0
+                    and bw.planes in (64, 128) and x.shape[3] <= 512):
+                # K1 writes the halo-padded layout; K2 reads every input pixel once (hg_conv3x3.cu)
+                a2h = arena.get_halo(bn_, bh_, bw_, bw.planes)
+                pixels = bn_ * bh_ * bw_
+                plan.meta.append(dict(op=f"conv1x1_k{x.shape[3]}_n{bw.planes}_{bh_}x{bw_}_pro_halo", kind="conv",
+                                      flops=2.0 * pixels * x.shape[3] * bw.planes,
+                                      bytes=pixels * (x.shape[3] + bw.planes) * 2 + bw.w1.numel() * 2))
+                L.append(lambda: ops.conv_nhwc(x, bw.w1, bw.b1, ksize=1, cout=bw.planes, relu=True, in_scale=bw.s1,
+                                               in_shift=bw.t1, out_halo=a2h))
+                a3 = arena.get((bn_, bh_, bw_, bw.planes))
+                plan.meta.append(dict(op=f"conv3x3h_k{9 * bw.planes}_n{bw.planes}_{bh_}x{bw_}", kind="conv",
+                                      flops=2.0 * pixels * 9 * bw.planes * bw.planes,
+                                      bytes=pixels * bw.planes * 4 + bw.w2.numel() * 2))
+                L.append(lambda: ops.conv3x3_halo(a2h, bw.w2, bw.b2, n=bn_, h=bh_, w=bw_, cin=bw.planes,
+                                                  cout=bw.planes, relu=True, out=a3))
+                arena.put_halo(a2h, bn_, bh_, bw_, bw.planes)
+            else:
+                a2 = conv(x, bw.w1, bw.b1, ksize=1, cout=bw.planes, relu=True, in_scale=bw.s1, in_shift=bw.t1)
+                a3 = conv(a2, bw.w2, bw.b2, ksize=3, cout=bw.planes, relu=True)
+                arena.put(a2)
             if bw.downsample:
                 out = conv(a3, bw.w3, bw.b3, ksize=1, cout=bw.cout, x2=x, up_low=up_low)
             else:

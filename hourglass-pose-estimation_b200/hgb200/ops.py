@@ -54,7 +54,8 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
               relu: bool = False, in_scale: Optional[torch.Tensor] = None, in_shift: Optional[torch.Tensor] = None,
               residual: Optional[torch.Tensor] = None, up_low: Optional[torch.Tensor] = None,
               x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-              out_nchw_f32: Optional[torch.Tensor] = None, heads: bool = False) -> torch.Tensor:
+              out_nchw_f32: Optional[torch.Tensor] = None, heads: bool = False,
+              out_halo: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Implicit-GEMM conv on tcgen05 (hg_conv_nhwc_bf16).
 
     x: bf16 [n,h,w,cin]; weight: bf16 [cout_pad, taps*cin (+cin2)]; bias fp32 [cout_pad].
@@ -71,6 +72,12 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
         raise HgError(f"conv_nhwc: weight {tuple(weight.shape)} / bias {bias.numel()} do not match "
                       f"[{cout_pad},{ktot}]")
     d = ConvDesc()
+    if out_halo is not None:
+        _require_cuda(out_halo)
+        if out_halo.dtype != torch.bfloat16 or out_halo.numel() != halo_padded_elems(n, h, w, cout) or heads:
+            raise HgError("conv_nhwc: out_halo must be a bf16 buffer of halo_padded_elems(n,h,w,cout) elements")
+        out = out_halo
+        d.out_halo = 1
     if heads:
         if out_nchw_f32 is None:
             out_nchw_f32 = torch.empty((n, cout, h, w), dtype=torch.float32, device=x.device)
@@ -79,6 +86,8 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
         if out is None:
             out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x.device)
         result = out
+    if ksize != 1 and out_halo is not None:
+        raise HgError("conv_nhwc: out_halo is a 1x1-conv output mode")
     for t, shape in ((residual, (n, h, w, cout)), (up_low, (n, h // 2, w // 2, cout)), (x2, (n, h, w, cin2))):
         if t is not None and (tuple(t.shape) != shape or t.dtype != torch.bfloat16):
             raise HgError(f"conv_nhwc: operand shape {tuple(t.shape)} != {shape} or not bf16")
@@ -104,6 +113,35 @@ def stem_im2col(x_nchw: torch.Tensor, flip_w: bool = False, out: Optional[torch.
     if out is None:
         out = torch.empty((n, h // 2, w // 2, 192), dtype=torch.bfloat16, device=x_nchw.device)
     lib.check(lib.hg_stem_im2col(_ptr(x_nchw), _ptr(out), n, h, w, int(flip_w), _stream()), "hg_stem_im2col")
+    return out
+
+
+def halo_padded_elems(n: int, h: int, w: int, c: int) -> int:
+    return (n * (h + 1) * (w + 1) + (w + 1)) * c
+
+
+def halo_padded_buffer(n: int, h: int, w: int, c: int, device) -> torch.Tensor:
+    """Zero-initialised flat bf16 buffer in the halo-padded layout [zero row][n][h+1][w+1][c]."""
+    return torch.zeros(halo_padded_elems(n, h, w, c), dtype=torch.bfloat16, device=device)
+
+
+def halo_interior(buf: torch.Tensor, n: int, h: int, w: int, c: int) -> torch.Tensor:
+    """Strided [n,h,w,c] view of the interior of a halo-padded buffer (tests / debugging)."""
+    return buf[(w + 1) * c:].view(n, h + 1, w + 1, c)[:, :h, :w, :]
+
+
+def conv3x3_halo(x_halo: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, n: int, h: int, w: int, cin: int,
+                 cout: int, relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 conv reading a halo-padded input (hg_conv3x3_halo_bf16) -> dense bf16 NHWC [n,h,w,cout]."""
+    _require_cuda(x_halo, weight, bias, out)
+    if x_halo.numel() != halo_padded_elems(n, h, w, cin) or x_halo.dtype != torch.bfloat16:
+        raise HgError("conv3x3_halo: input is not a halo-padded bf16 buffer of the stated shape")
+    if tuple(weight.shape) != (cout, 9 * cin) or weight.dtype != torch.bfloat16 or bias.numel() < cout:
+        raise HgError(f"conv3x3_halo: weight {tuple(weight.shape)} != [{cout},{9 * cin}]")
+    if out is None:
+        out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x_halo.device)
+    lib.check(lib.hg_conv3x3_halo_bf16(_ptr(x_halo), _ptr(weight), _ptr(bias), _ptr(out), _ptr(err_word(x_halo.device)),
+                                       n, h, w, cin, cout, int(relu), _stream()), "hg_conv3x3_halo_bf16")
     return out
 
 

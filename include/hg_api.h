@@ -33,7 +33,7 @@ extern "C" {
 #define HG_ERR_ARCH (-3)     /* device is not sm_100 */
 #define HG_ERR_DEVICE (-4)   /* a kernel reported a protocol timeout through its error word */
 
-#define HG_API_VERSION 1
+#define HG_API_VERSION 2
 
 int hg_api_version(void);
 /* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
@@ -72,9 +72,21 @@ typedef struct hg_conv_desc {
     int32_t cin, cin2, cout;
     int32_t ksize;           /* 1 or 3 (stride 1, pad ksize/2)                                  */
     int32_t relu;            /* apply ReLU in the epilogue                                      */
+    int32_t out_halo;        /* 1: `out` is a HALO-PADDED buffer (see hg_conv3x3_halo_bf16); 1x1 only,
+                                needs 128 %% w == 0 and (h*w) %% 128 == 0                          */
 } hg_conv_desc;
 
 int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream);
+
+/* 3x3 convolution (stride 1, pad 1) + bias (+ReLU) reading a HALO-PADDED input: a bf16 buffer of
+ * hg_halo_padded_elems(n,h,w,c) elements laid out as [1 zero row of (w+1) pixels][n][h+1][w+1][c], i.e. one zero
+ * column right of every image row and one zero row under every image.  The caller zero-initialises the
+ * buffer ONCE; producers (hg_conv_nhwc_bf16 with out_halo=1) only ever write the interior.  In this layout
+ * every filter tap is a constant offset, so each input pixel is fetched once per tile instead of nine times.
+ * weight: bf16 [cout][9*cin], k = (ky*3+kx)*cin + c; out: dense bf16 NHWC [n][h][w][cout]; cout in {64,128}. */
+int64_t hg_halo_padded_elems(int32_t n, int32_t h, int32_t w, int32_t c);
+int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, const float* bias, void* out, unsigned int* err_word,
+                         int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t relu, void* stream);
 
 /* Stem: conv 7x7 stride 2 pad 3 (3 -> cout) + folded BN + ReLU (src/models/hourglass.py:71-73).
  * Step 1 gathers NCHW fp32 pixels into K-major bf16 rows [n*oh*ow][192] (k = (ky*7+kx)*3 + c,

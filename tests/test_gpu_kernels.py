@@ -71,6 +71,48 @@ def test_stem_im2col_and_gemm(ops, dev):
         assert err <= float(ref.abs().max()) * 2 ** -7
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 64, 128, 128), (3, 32, 32, 128, 128), (1, 128, 128, 64, 64), (5, 16, 16, 128, 128),
+                                   (2, 64, 48, 128, 128), (7, 8, 8, 64, 128), (40, 64, 64, 128, 128), (3, 10, 6, 128, 64)])
+def test_conv3x3_halo(shape, ops, dev):
+    """Second-generation 3x3: halo-padded input, every tap a shifted descriptor into ONE smem tile."""
+    no_tf32()
+    n, h, w, cin, cout = shape
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5))
+    bias = (torch.randn(cout, generator=g) * 0.5).to(dev)
+    buf = ops.halo_padded_buffer(n, h, w, cin, dev)
+    ops.halo_interior(buf, n, h, w, cin).copy_(x.to(dev))
+    wmat = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).to(torch.bfloat16).to(dev)
+    out = ops.conv3x3_halo(buf, wmat, bias, n=n, h=h, w=w, cin=cin, cout=cout, relu=True)
+    torch.cuda.synchronize()
+    ops.check_err_word(dev)
+    ref = F.relu(F.conv2d(x.float().to(dev).permute(0, 3, 1, 2), r16(wt).to(dev), bias, padding=1))
+    err = float((out.float().permute(0, 3, 1, 2) - ref).abs().max())
+    assert err <= float(ref.abs().max()) * 2 ** -7, f"err {err} vs scale {float(ref.abs().max())}"
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 64, 256, 128), (3, 32, 32, 256, 128), (1, 128, 128, 64, 64), (4, 16, 16, 256, 128)])
+def test_conv1x1_writes_halo_padded_output(shape, ops, dev):
+    no_tf32()
+    n, h, w, cin, cout = shape
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).to(dev)
+    wt = (torch.randn(cout, cin, generator=g) / cin ** 0.5).to(torch.bfloat16).to(dev)
+    bias = (torch.randn(cout, generator=g) * 0.5).to(dev)
+    scale = (0.5 + torch.rand(cin, generator=g)).to(dev)
+    shift = (0.3 * torch.randn(cin, generator=g)).to(dev)
+    dense = ops.conv_nhwc(x, wt, bias, ksize=1, cout=cout, relu=True, in_scale=scale, in_shift=shift)
+    buf = ops.halo_padded_buffer(n, h, w, cout, dev)
+    ops.conv_nhwc(x, wt, bias, ksize=1, cout=cout, relu=True, in_scale=scale, in_shift=shift, out_halo=buf)
+    torch.cuda.synchronize()
+    ops.check_err_word(dev)
+    assert torch.equal(ops.halo_interior(buf, n, h, w, cout), dense)
+    full = buf[(w + 1) * cout:].view(n, h + 1, w + 1, cout)
+    assert float(full[:, h].abs().max()) == 0 and float(full[:, :, w].abs().max()) == 0      # pads untouched
+    assert float(buf[:(w + 1) * cout].abs().max()) == 0
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 96), (1, 256, 256), (2, 256, 192), (3, 128, 512)])
 def test_stem_window_conv(shape, ops, dev):
     """7x7/s2 stem through the overlapping-window TMA path (no im2col matrix)."""
