@@ -244,8 +244,9 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
             for (int slab = 0; slab < kSlabs; ++slab) {
                 ok = mbar_wait(&res_full_bar[buf], ring_phase, p.err_word, kErrEpilogue | 2);
                 if (!ok) break;
-                uint8_t* stg = smem_ring + buf * kSlabBytes + row * 128;
-                const uint8_t* upb = smem_up + buf * kUpBytes + low_row * 128;
+                const uint32_t stg = smem_u32(smem_ring + buf * kSlabBytes + row * 128);
+                const uint32_t upb = smem_u32(smem_up + buf * kUpBytes + low_row * 128);
+                const uint32_t bias_s = smem_u32(s_bias);
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int col0 = slab * 64 + half * 32;
@@ -254,13 +255,20 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                     uint4 r_res[4], r_up[4];
                     if (p.has_res) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            r_res[i] = *reinterpret_cast<const uint4*>(stg + (((half * 4 + i) ^ (row & 7)) << 4));
+                        for (int i = 0; i < 4; ++i) r_res[i] = lds128(stg + (((half * 4 + i) ^ (row & 7)) << 4));
                     }
                     if (p.has_up) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            r_up[i] = *reinterpret_cast<const uint4*>(upb + (((half * 4 + i) ^ (low_row & 7)) << 4));
+                        for (int i = 0; i < 4; ++i) r_up[i] = lds128(upb + (((half * 4 + i) ^ (low_row & 7)) << 4));
+                    }
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {       // warp-uniform address: one broadcast wavefront per 4 channels
+                        const float4 b4 = lds128f(bias_s + (col0 + i * 4) * 4);
+                        f[i * 4 + 0] = b4.x;
+                        f[i * 4 + 1] = b4.y;
+                        f[i * 4 + 2] = b4.z;
+                        f[i * 4 + 3] = b4.w;
                     }
                     tmem_ld_wait();
                     if (slab == kSlabs - 1 && half == 1) {
@@ -268,9 +276,8 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                     }
-                    float f[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + s_bias[col0 + i];
+                    for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]);
                     if (p.has_res) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -293,18 +300,21 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                             }
                         }
                     }
-                    if (p.relu) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-                    }
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         uint4 o;
-                        o.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]);
-                        o.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
-                        o.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]);
-                        o.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
-                        *reinterpret_cast<uint4*>(stg + (((half * 4 + i) ^ (row & 7)) << 4)) = o;
+                        if (p.relu) {
+                            o.x = pack_bf16x2_relu(f[i * 8 + 0], f[i * 8 + 1]);
+                            o.y = pack_bf16x2_relu(f[i * 8 + 2], f[i * 8 + 3]);
+                            o.z = pack_bf16x2_relu(f[i * 8 + 4], f[i * 8 + 5]);
+                            o.w = pack_bf16x2_relu(f[i * 8 + 6], f[i * 8 + 7]);
+                        } else {
+                            o.x = pack_bf16x2(f[i * 8 + 0], f[i * 8 + 1]);
+                            o.y = pack_bf16x2(f[i * 8 + 2], f[i * 8 + 3]);
+                            o.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]);
+                            o.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
+                        }
+                        sts128(stg + (((half * 4 + i) ^ (row & 7)) << 4), o);
                     }
                 }
                 fence_proxy_async_smem();
@@ -345,26 +355,27 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                 ok = mbar_wait(&full_bar[stage], phase, p.err_word, kErrPrologue | 1);
                 if (!ok) break;
                 if (kb < p.kb1) {
-                    const int c0 = kb * kBlockK + c * 8;
-                    const float4 s0 = *reinterpret_cast<const float4*>(s_scale + c0);
-                    const float4 s1 = *reinterpret_cast<const float4*>(s_scale + c0 + 4);
-                    const float4 h0 = *reinterpret_cast<const float4*>(s_shift + c0);
-                    const float4 h1 = *reinterpret_cast<const float4*>(s_shift + c0 + 4);
-                    uint8_t* a_base = smem_a + stage * kSlabBytes;
+                    const uint32_t sc = smem_u32(s_scale + kb * kBlockK + c * 8);
+                    const uint32_t sh = smem_u32(s_shift + kb * kBlockK + c * 8);
+                    const float4 s0 = lds128f(sc), s1 = lds128f(sc + 16);
+                    const float4 h0 = lds128f(sh), h1 = lds128f(sh + 16);
+                    const uint32_t a_base = smem_u32(smem_a + stage * kSlabBytes);
+                    uint32_t addr[8];
+                    uint4 d[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {                        // all eight loads in flight before any use
+                        const int row = i * 16 + w * 4 + rsub;           // a quarter-warp owns one 128-byte row
+                        addr[i] = a_base + row * 128 + ((c ^ (row & 7)) << 4);
+                        d[i] = lds128(addr[i]);
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int row = i * 16 + w * 4 + rsub;           // a quarter-warp owns one 128-byte row
-                        uint4* ptr = reinterpret_cast<uint4*>(a_base + row * 128 + ((c ^ (row & 7)) << 4));
-                        uint4 d = *ptr;
-                        d.x = pack_bf16x2(fmaxf(fmaf(bf16_lo_to_f32(d.x), s0.x, h0.x), 0.f),
-                                          fmaxf(fmaf(bf16_hi_to_f32(d.x), s0.y, h0.y), 0.f));
-                        d.y = pack_bf16x2(fmaxf(fmaf(bf16_lo_to_f32(d.y), s0.z, h0.z), 0.f),
-                                          fmaxf(fmaf(bf16_hi_to_f32(d.y), s0.w, h0.w), 0.f));
-                        d.z = pack_bf16x2(fmaxf(fmaf(bf16_lo_to_f32(d.z), s1.x, h1.x), 0.f),
-                                          fmaxf(fmaf(bf16_hi_to_f32(d.z), s1.y, h1.y), 0.f));
-                        d.w = pack_bf16x2(fmaxf(fmaf(bf16_lo_to_f32(d.w), s1.z, h1.z), 0.f),
-                                          fmaxf(fmaf(bf16_hi_to_f32(d.w), s1.w, h1.w), 0.f));
-                        *ptr = d;
+                        uint4 o;
+                        o.x = pack_bf16x2_relu(fmaf(bf16_lo_to_f32(d[i].x), s0.x, h0.x), fmaf(bf16_hi_to_f32(d[i].x), s0.y, h0.y));
+                        o.y = pack_bf16x2_relu(fmaf(bf16_lo_to_f32(d[i].y), s0.z, h0.z), fmaf(bf16_hi_to_f32(d[i].y), s0.w, h0.w));
+                        o.z = pack_bf16x2_relu(fmaf(bf16_lo_to_f32(d[i].z), s1.x, h1.x), fmaf(bf16_hi_to_f32(d[i].z), s1.y, h1.y));
+                        o.w = pack_bf16x2_relu(fmaf(bf16_lo_to_f32(d[i].w), s1.z, h1.z), fmaf(bf16_hi_to_f32(d[i].w), s1.w, h1.w));
+                        sts128(addr[i], o);
                     }
                     fence_proxy_async_smem();
                 }
