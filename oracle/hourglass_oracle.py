@@ -23,10 +23,17 @@ BN_EPS = 1e-5  # torch.nn.BatchNorm2d default used everywhere in the reference
 
 
 _CALIBRATE = [False]
+_TRAINING = [False]      # train-mode BatchNorm (batch statistics + running-stat update), see oracle/train_oracle.py
+BN_MOMENTUM = 0.1        # nn.BatchNorm2d default used everywhere in the reference
 
 
 def _bn(sd: Dict[str, torch.Tensor], p: str, x: torch.Tensor) -> torch.Tensor:
-    """Eval-mode BatchNorm2d with running statistics."""
+    """BatchNorm2d: running statistics in eval mode; batch statistics (biased variance for the
+    normalisation, unbiased for the running-variance update, momentum 0.1) in train mode."""
+    if _TRAINING[0]:
+        sd[p + ".num_batches_tracked"] = sd[p + ".num_batches_tracked"] + 1
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"],
+                            sd[p + ".weight"], sd[p + ".bias"], True, BN_MOMENTUM, BN_EPS)
     if _CALIBRATE[0]:   # see calibrate_bn(): overwrite running stats with this batch's statistics
         sd[p + ".running_mean"] = x.mean(dim=(0, 2, 3))
         sd[p + ".running_var"] = x.var(dim=(0, 2, 3), unbiased=False)

@@ -138,6 +138,42 @@ def loss_golden():
     print("loss cases", len(cases))
 
 
+from oracle.make_golden_inputs import train_inputs, TRAIN_STRIDE  # noqa: E402
+
+
+def train_golden(name="train_s2_j16_128", num_stacks=2, J=16, B=4, H=128, W=128, seed=7, steps=2, lr=2.5e-4):
+    """Two steps of the reference's training loop body (trainer.py:89-99): model.train(), MSELoss(True),
+    loss.backward(), RMSprop(lr).step().  Stores losses, strided samples of the last step's gradients, of the
+    updated parameters and of the BN running statistics."""
+    sd = make_state_dict(num_stacks=num_stacks, num_blocks=1, num_classes=J, seed=seed)
+    model = ref_hg(num_stacks=num_stacks, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum")
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    crit = RefMSELoss(use_target_weight=True)
+    opt = torch.optim.RMSprop(model.parameters(), lr=lr, momentum=0, weight_decay=0)
+    losses = []
+    for x, tg, tw in train_inputs(seed + 1, B, J, H, W, steps):
+        outs = model(x)
+        loss = crit(outs, tg, tw)
+        opt.zero_grad()
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        opt.step()
+        losses.append(float(loss.detach()))
+    out = {"cfg": np.array([num_stacks, J, B, H, W, seed, steps]), "lr": np.array(lr), "losses": np.array(losses),
+           "stride": np.array(TRAIN_STRIDE)}
+    keys = sorted(grads)
+    out["grad_sample"] = np.concatenate([grads[k].reshape(-1).numpy() for k in keys])[::TRAIN_STRIDE].copy()
+    out["grad_norms"] = np.array([float(grads[k].norm()) for k in keys])
+    fsd = model.state_dict()
+    out["param_sample"] = np.concatenate([fsd[k].reshape(-1).float().numpy() for k in keys])[::TRAIN_STRIDE].copy()
+    bkeys = sorted(k for k in fsd if k.endswith("running_mean") or k.endswith("running_var"))
+    out["stat_sample"] = np.concatenate([fsd[k].reshape(-1).numpy() for k in bkeys])[::7].copy()
+    out["heat_last"] = outs[-1].detach().numpy()[:, :, ::4, ::4].copy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "losses", losses, "params", len(keys))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     # C1-shaped (2-stack, 256x256, B=1) plus small/variant shapes
@@ -149,3 +185,4 @@ if __name__ == "__main__":
     model_case("model_s1_j16_64_nb2", 1, 16, 1, 64, 64, seed=5, num_blocks=2)
     decode_golden()
     loss_golden()
+    train_golden()
