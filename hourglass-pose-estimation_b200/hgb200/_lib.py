@@ -28,6 +28,16 @@ class ConvDesc(C.Structure):
     ]
 
 
+class PackEntry(C.Structure):
+    """struct hg_pack_entry"""
+    _fields_ = [
+        ("src", C.c_void_p), ("src2", C.c_void_p), ("dst_f32", C.c_void_p), ("dst_fwd", C.c_void_p),
+        ("dst_dgrad", C.c_void_p),
+        ("co", C.c_int32), ("taps", C.c_int32), ("ci", C.c_int32),
+        ("fwd_ld", C.c_int32), ("fwd_col0", C.c_int32), ("dgrad_ld", C.c_int32),
+    ]
+
+
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 _SIGNATURES = {
@@ -53,6 +63,19 @@ _SIGNATURES = {
     "hg_gaussian_target": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_jmse_loss": ([C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32,
                       _f32, _vp], C.c_int),
+    "hg_colstats_nhwc": ([_vp, _vp, _vp, _i64, _i32, _i32, _vp], C.c_int),
+    "hg_bn_train_fwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp],
+                        C.c_int),
+    "hg_bn_bwd_reduce": ([_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp], C.c_int),
+    "hg_bn_bwd_apply": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_maxpool2x2_bwd_nhwc": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_sumpool2x2_nhwc": ([_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_add_inplace_bf16": ([_vp, _vp, _i64, _vp], C.c_int),
+    "hg_nchw_f32_to_nhwc_bf16_pad": ([_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_pack_weights": ([_vp, _i32, _vp], C.c_int),
+    "hg_rmsprop_step": ([_vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp], C.c_int),
+    "hg_small_gemm_f32": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp], C.c_int),
+    "hg_wgrad_bf16": ([_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

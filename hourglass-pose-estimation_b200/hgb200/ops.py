@@ -7,7 +7,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from ._lib import lib, ConvDesc, HgError
+from ._lib import lib, ConvDesc, PackEntry, HgError
 
 _err_words = {}
 
@@ -62,15 +62,15 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
     heads=True -> returns fp32 NCHW [n,cout,h,w]; else bf16 NHWC [n,h,w,cout].
     """
     _require_cuda(x, weight, bias, in_scale, in_shift, residual, up_low, x2, out, out_nchw_f32)
-    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or bias.dtype != torch.float32:
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or (bias is not None and bias.dtype != torch.float32):
         raise HgError("conv_nhwc: x/weight must be bf16 and bias fp32")
     n, h, w, cin = x.shape
     cin2 = 0 if x2 is None else x2.shape[-1]
     cout_pad = (cout + 15) // 16 * 16
     ktot = ksize * ksize * cin + cin2
-    if tuple(weight.shape) != (cout_pad, ktot) or bias.numel() != cout_pad:
-        raise HgError(f"conv_nhwc: weight {tuple(weight.shape)} / bias {bias.numel()} do not match "
-                      f"[{cout_pad},{ktot}]")
+    if tuple(weight.shape) != (cout_pad, ktot) or (bias is not None and bias.numel() < cout_pad):
+        raise HgError(f"conv_nhwc: weight {tuple(weight.shape)} / bias {None if bias is None else bias.numel()} do not "
+                      f"match [{cout_pad},{ktot}]")
     d = ConvDesc()
     if out_halo is not None:
         _require_cuda(out_halo)
@@ -91,7 +91,8 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
     for t, shape in ((residual, (n, h, w, cout)), (up_low, (n, h // 2, w // 2, cout)), (x2, (n, h, w, cin2))):
         if t is not None and (tuple(t.shape) != shape or t.dtype != torch.bfloat16):
             raise HgError(f"conv_nhwc: operand shape {tuple(t.shape)} != {shape} or not bf16")
-    d.in_, d.in2, d.weight, d.bias = x.data_ptr(), (x2.data_ptr() if x2 is not None else None), weight.data_ptr(), bias.data_ptr()
+    d.in_, d.in2, d.weight = x.data_ptr(), (x2.data_ptr() if x2 is not None else None), weight.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
     d.in_scale = in_scale.data_ptr() if in_scale is not None else None
     d.in_shift = in_shift.data_ptr() if in_shift is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
@@ -136,7 +137,7 @@ def conv3x3_halo(x_halo: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
     _require_cuda(x_halo, weight, bias, out)
     if x_halo.numel() != halo_padded_elems(n, h, w, cin) or x_halo.dtype != torch.bfloat16:
         raise HgError("conv3x3_halo: input is not a halo-padded bf16 buffer of the stated shape")
-    if tuple(weight.shape) != (cout, 9 * cin) or weight.dtype != torch.bfloat16 or bias.numel() < cout:
+    if tuple(weight.shape) != (cout, 9 * cin) or weight.dtype != torch.bfloat16 or (bias is not None and bias.numel() < cout):
         raise HgError(f"conv3x3_halo: weight {tuple(weight.shape)} != [{cout},{9 * cin}]")
     if out is None:
         out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x_halo.device)
@@ -340,3 +341,145 @@ def jmse_loss(preds: Sequence[torch.Tensor], target: Optional[torch.Tensor], tar
     lib.check(lib.hg_jmse_loss(parr, garr, _ptr(target), _ptr(tw), _ptr(mu), _ptr(patch), int(sigma * 3), _ptr(loss), S,
                                b, j, h, w, C.c_float(grad_scale), _stream()), "hg_jmse_loss")
     return loss, grads
+
+
+# ------------------------------------------------------------------------------------------------ training
+def wgrad(dout: torch.Tensor, z: torch.Tensor, dw: torch.Tensor, *, co_valid: Optional[int] = None,
+          ci_valid: Optional[int] = None, taps: int = 1, halo_pitch: int = 0, ld: Optional[int] = None,
+          tap_stride: Optional[int] = None) -> torch.Tensor:
+    """dw (fp32, pre-zeroed or partial) += dout^T . z over rows (hg_wgrad_bf16).
+
+    dout: bf16 [..., co], z: bf16 [..., ci] with the same number of rows (taps=9: both halo-padded flat
+    buffers incl. the leading zero row).  dw rows are `ld` floats apart, taps `tap_stride` apart."""
+    _require_cuda(dout, z, dw)
+    if dout.dtype != torch.bfloat16 or z.dtype != torch.bfloat16 or dw.dtype != torch.float32:
+        raise HgError("wgrad: dout/z must be bf16, dw fp32")
+    co, ci = dout.shape[-1], z.shape[-1]
+    rows = dout.numel() // co
+    if z.numel() // ci != rows:
+        raise HgError(f"wgrad: row counts differ ({rows} vs {z.numel() // ci})")
+    ci_valid = ci if ci_valid is None else ci_valid
+    co_valid = co if co_valid is None else co_valid
+    tap_stride = ci_valid if tap_stride is None else tap_stride
+    ld = taps * tap_stride if ld is None else ld
+    if dw.numel() < (co_valid - 1) * ld + (taps - 1) * tap_stride + ci_valid:
+        raise HgError("wgrad: dw too small")
+    lib.check(lib.hg_wgrad_bf16(_ptr(dout), _ptr(z), _ptr(dw), _ptr(err_word(dout.device)), rows, co, co_valid, ci,
+                                ci_valid, taps, halo_pitch, ld, tap_stride, _stream()), "hg_wgrad_bf16")
+    return dw
+
+
+def colstats(x: torch.Tensor, sum_out: torch.Tensor, sumsq_out: Optional[torch.Tensor] = None, c_valid: Optional[int] = None):
+    """sum_out[c] += sum over pixels of x[..., c] (and sumsq_out[c] += sum of squares); x bf16 NHWC."""
+    _require_cuda(x, sum_out, sumsq_out)
+    c = x.shape[-1]
+    lib.check(lib.hg_colstats_nhwc(_ptr(x), _ptr(sum_out), _ptr(sumsq_out), x.numel() // c, c, c if c_valid is None else c_valid,
+                                   _stream()), "hg_colstats_nhwc")
+
+
+def bn_train_fwd(x: torch.Tensor, sums: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                 running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
+                 num_batches_tracked: Optional[torch.Tensor], saved: torch.Tensor, out: torch.Tensor, *, halo: bool = False,
+                 relu: bool = True, eps: float = 1e-5, momentum: float = 0.1):
+    """Train-mode BatchNorm2d(+ReLU) of a dense bf16 NHWC tensor from batch sums (hg_bn_train_fwd)."""
+    _require_cuda(x, sums, gamma, beta, running_mean, running_var, num_batches_tracked, saved, out)
+    n, h, w, c = x.shape
+    lib.check(lib.hg_bn_train_fwd(_ptr(x), _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+                                  _ptr(num_batches_tracked), _ptr(saved), _ptr(out), n, h, w, c, int(halo), int(relu),
+                                  C.c_float(eps), C.c_float(momentum), _stream()), "hg_bn_train_fwd")
+    return out
+
+
+def bn_bwd_reduce(dz: torch.Tensor, x: torch.Tensor, saved: torch.Tensor, sums: torch.Tensor, relu: bool = True):
+    _require_cuda(dz, x, saved, sums)
+    c = x.shape[-1]
+    lib.check(lib.hg_bn_bwd_reduce(_ptr(dz), _ptr(x), _ptr(saved), _ptr(sums), x.numel() // c, c, int(relu), _stream()),
+              "hg_bn_bwd_reduce")
+
+
+def bn_bwd_apply(dz: torch.Tensor, x: torch.Tensor, saved: torch.Tensor, sums: torch.Tensor, out: torch.Tensor, *,
+                 add1: Optional[torch.Tensor] = None, add2: Optional[torch.Tensor] = None,
+                 dgamma: Optional[torch.Tensor] = None, dbeta: Optional[torch.Tensor] = None, halo: bool = False,
+                 relu: bool = True):
+    _require_cuda(dz, x, saved, sums, out, add1, add2, dgamma, dbeta)
+    n, h, w, c = x.shape
+    lib.check(lib.hg_bn_bwd_apply(_ptr(dz), _ptr(x), _ptr(saved), _ptr(sums), _ptr(add1), _ptr(add2), _ptr(out), _ptr(dgamma),
+                                  _ptr(dbeta), n, h, w, c, int(halo), int(relu), _stream()), "hg_bn_bwd_apply")
+    return out
+
+
+def maxpool2x2_bwd(x: torch.Tensor, dpool: torch.Tensor, dx: torch.Tensor, accumulate: bool):
+    _require_cuda(x, dpool, dx)
+    n, h, w, c = x.shape
+    lib.check(lib.hg_maxpool2x2_bwd_nhwc(_ptr(x), _ptr(dpool), _ptr(dx), n, h, w, c, int(accumulate), _stream()),
+              "hg_maxpool2x2_bwd_nhwc")
+    return dx
+
+
+def sumpool2x2(dy: torch.Tensor, dlow: torch.Tensor, accumulate: bool = False):
+    _require_cuda(dy, dlow)
+    n, h, w, c = dy.shape
+    lib.check(lib.hg_sumpool2x2_nhwc(_ptr(dy), _ptr(dlow), n, h, w, c, int(accumulate), _stream()), "hg_sumpool2x2_nhwc")
+    return dlow
+
+
+def add_inplace(dst: torch.Tensor, src: torch.Tensor):
+    _require_cuda(dst, src)
+    lib.check(lib.hg_add_inplace_bf16(_ptr(dst), _ptr(src), dst.numel(), _stream()), "hg_add_inplace_bf16")
+    return dst
+
+
+def nchw_to_nhwc_bf16_pad(x: torch.Tensor, out: torch.Tensor):
+    """fp32 NCHW [n,c,h,w] -> bf16 NHWC [n,h,w,c_pad] (zero-padded channels)."""
+    _require_cuda(x, out)
+    n, c, h, w = x.shape
+    lib.check(lib.hg_nchw_f32_to_nhwc_bf16_pad(_ptr(x), _ptr(out), n, c, out.shape[-1], h, w, _stream()),
+              "hg_nchw_f32_to_nhwc_bf16_pad")
+    return out
+
+
+def make_pack_table(entries, device) -> torch.Tensor:
+    """entries: list of dicts(src, src2, dst_f32, dst_fwd, dst_dgrad: tensors or None; co, taps, ci, fwd_ld, fwd_col0,
+    dgrad_ld) -> device uint8 tensor holding the hg_pack_entry array."""
+    arr = (PackEntry * len(entries))()
+    for a, e in zip(arr, entries):
+        for k in ("src", "src2", "dst_f32", "dst_fwd", "dst_dgrad"):
+            t = e.get(k)
+            setattr(a, k, t.data_ptr() if t is not None else None)
+        for k in ("co", "taps", "ci", "fwd_ld", "fwd_col0", "dgrad_ld"):
+            setattr(a, k, int(e.get(k, 0)))
+    raw = bytes(arr)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
+def pack_weights(table: torch.Tensor, n_entries: int):
+    _require_cuda(table)
+    lib.check(lib.hg_pack_weights(_ptr(table), n_entries, _stream()), "hg_pack_weights")
+
+
+def rmsprop_step(params: torch.Tensor, grads: torch.Tensor, square_avg: torch.Tensor, lr: float, alpha: float = 0.99,
+                 eps: float = 1e-8, grad_scale: float = 1.0):
+    _require_cuda(params, grads, square_avg)
+    lib.check(lib.hg_rmsprop_step(_ptr(params), _ptr(grads), _ptr(square_avg), params.numel(), C.c_float(lr),
+                                  C.c_float(alpha), C.c_float(eps), C.c_float(grad_scale), _stream()), "hg_rmsprop_step")
+
+
+def small_gemm(c: torch.Tensor, a: torch.Tensor, b: torch.Tensor, d: Optional[torch.Tensor], m: int, n: int, k: int,
+               sai: int, sak: int, sbk: int, sbj: int, sci: int, scj: int, beta: float = 0.0):
+    _require_cuda(c, a, b, d)
+    lib.check(lib.hg_small_gemm_f32(_ptr(c), _ptr(a), _ptr(b), _ptr(d), m, n, k, sai, sak, sbk, sbj, sci, scj,
+                                    C.c_float(beta), _stream()), "hg_small_gemm_f32")
+
+
+def jmse_loss_into(preds: Sequence[torch.Tensor], grads: Optional[Sequence[torch.Tensor]], target: Optional[torch.Tensor],
+                   target_weight: Optional[torch.Tensor], loss_out: torch.Tensor, *, grad_scale: float = 1.0,
+                   mu: Optional[torch.Tensor] = None, sigma=1):
+    """Pointer-stable form of jmse_loss for static plans: loss_out (fp32 [1]) must be zeroed by the caller."""
+    _require_cuda(*preds, target, target_weight, mu, loss_out)
+    b, j, h, w = preds[0].shape
+    S = len(preds)
+    parr = (C.c_void_p * S)(*[p.data_ptr() for p in preds])
+    garr = (C.c_void_p * S)(*[g.data_ptr() for g in grads]) if grads is not None else None
+    patch = gaussian_patch(sigma, preds[0].device) if target is None else None
+    lib.check(lib.hg_jmse_loss(parr, garr, _ptr(target), _ptr(target_weight), _ptr(mu), _ptr(patch), int(sigma * 3),
+                               _ptr(loss_out), S, b, j, h, w, C.c_float(grad_scale), _stream()), "hg_jmse_loss")

@@ -33,7 +33,7 @@ extern "C" {
 #define HG_ERR_ARCH (-3)     /* device is not sm_100 */
 #define HG_ERR_DEVICE (-4)   /* a kernel reported a protocol timeout through its error word */
 
-#define HG_API_VERSION 2
+#define HG_API_VERSION 3
 
 int hg_api_version(void);
 /* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
@@ -165,6 +165,90 @@ int hg_gaussian_target(const int32_t* mu, const float* weight, const float* patc
 int hg_jmse_loss(const float* const* preds, float* const* grads, const float* target, const float* target_weight,
                  const int32_t* mu, const float* patch, int32_t radius, float* loss_out, int32_t stacks, int32_t b,
                  int32_t j, int32_t h, int32_t w, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------- *
+ * Training (src/runner/trainer.py:82-99: loss.backward() + optimizer.step()).
+ * Gradients w.r.t. activations ("dgrad") reuse hg_conv_nhwc_bf16 / hg_conv3x3_halo_bf16 on transposed
+ * (3x3: also tap-flipped) weight copies; the entries below are the rest of the backward pass.
+ * ------------------------------------------------------------------------------------------- */
+/* conv.weight.grad as a split-K tcgen05 GEMM over pixels, reading both NHWC operands as they lie
+ * (MN-major UMMA descriptors):  dw[o*ld + tap*tap_stride + i] += sum_f dout[f][o] * z[f + off(tap)][i]
+ * for o < co_valid, i < ci_valid.  dout: bf16 [rows][co], z: bf16 [rows][ci]; dw is fp32 and must be
+ * zero-initialised (or hold a partial sum): CTAs add with red.global.
+ * taps == 1: off = 0.  taps == 9: both tensors are halo-padded buffers of identical geometry
+ * (hg_conv3x3_halo_bf16) INCLUDING the leading zero row, rows = all positions, halo_pitch = w+1,
+ * off(tap) = (tap/3-1)*halo_pitch + tap%3-1.   co <= 256 (multiple of 8), ci in {64,128,192,256}. */
+int hg_wgrad_bf16(const void* dout, const void* z, float* dw, unsigned int* err_word, int64_t rows, int32_t co,
+                  int32_t co_valid, int32_t ci, int32_t ci_valid, int32_t taps, int32_t halo_pitch, int32_t ld,
+                  int32_t tap_stride, void* stream);
+
+/* Per-channel sum (and sum of squares) over the pixels of an NHWC bf16 tensor, ADDED into fp32
+ * accumulators (zeroed by the caller): batch statistics of nn.BatchNorm2d in train mode, and conv.bias.grad.
+ * sumsq may be NULL; channels >= c_valid are skipped.  c in {64,128,256}. */
+int hg_colstats_nhwc(const void* x, float* sum, float* sumsq, int64_t pixels, int32_t c, int32_t c_valid, void* stream);
+
+/* Train-mode BatchNorm2d (+ReLU) forward from batch sums (sums = [sum | sumsq], 2c floats):
+ * out = [relu]((x - mean) * invstd * gamma + beta), biased variance, eps as given (torch: 1e-5).
+ * Also writes saved = [mean | invstd | scale | shift] (4c floats, read by the backward kernels) and, when
+ * running_mean != NULL, updates running_mean / running_var (unbiased) with `momentum` and increments
+ * *num_batches_tracked (int64, may be NULL).   out_halo != 0: `out` is a halo-padded buffer (interior only
+ * is written).  Reference: the BatchNorm2d modules of src/models/modules.py:11-19 under model.train(). */
+int hg_bn_train_fwd(const void* x, const float* sums, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, int64_t* num_batches_tracked, float* saved, void* out, int32_t n, int32_t h,
+                    int32_t w, int32_t c, int32_t out_halo, int32_t relu, float eps, float momentum, void* stream);
+
+/* BatchNorm2d(+ReLU) backward.  Pass 1 adds s1 = sum dY and s2 = sum dY*xhat into sums (2c floats, zeroed by the
+ * caller), dY = dz masked by the recomputed ReLU.  Pass 2 writes
+ *   out = scale*(dY - s1/N - xhat*s2/N) [+ add1] [+ add2]       (bf16 NHWC, or halo-padded when out_halo)
+ * and dgamma = s2, dbeta = s1 (fp32 [c], may both be NULL).  `out` may alias add1/add2 (element-wise in place). */
+int hg_bn_bwd_reduce(const void* dz, const void* x, const float* saved, float* sums, int64_t pixels, int32_t c,
+                     int32_t relu, void* stream);
+int hg_bn_bwd_apply(const void* dz, const void* x, const float* saved, const float* sums, const void* add1,
+                    const void* add2, void* out, float* dgamma, float* dbeta, int32_t n, int32_t h, int32_t w, int32_t c,
+                    int32_t out_halo, int32_t relu, void* stream);
+
+/* F.max_pool2d(x,2,2) backward: dx (+)= dpool routed to the first maximum of each window (torch's rule).
+ * With accumulate == 0 every element of dx is written.  src/models/modules.py:82, hourglass.py:76. */
+int hg_maxpool2x2_bwd_nhwc(const void* x, const void* dpool, void* dx, int32_t n, int32_t h, int32_t w, int32_t c,
+                           int32_t accumulate, void* stream);
+/* F.interpolate(scale_factor=2, nearest) backward: dlow (+)= 2x2 sums of dy [n][h][w][c].  modules.py:90. */
+int hg_sumpool2x2_nhwc(const void* dy, void* dlow, int32_t n, int32_t h, int32_t w, int32_t c, int32_t accumulate,
+                       void* stream);
+/* dst += src (bf16, fp32 add, one rounding): gradient fan-in of the residual stream. */
+int hg_add_inplace_bf16(void* dst, const void* src, int64_t count, void* stream);
+/* fp32 NCHW [n][c][h][w] -> bf16 NHWC [n][h][w][c_pad] with zero channels c..c_pad (heat-map gradients as a
+ * GEMM operand). */
+int hg_nchw_f32_to_nhwc_bf16_pad(const float* in, void* out, int32_t n, int32_t c, int32_t c_pad, int32_t h, int32_t w,
+                                 void* stream);
+
+/* Weight packing, one launch for the whole network.  Every entry converts one fp32 master tensor
+ * [co][taps][ci] (GEMM-natural order = torch channels_last) (+ optional src2, added element-wise) into
+ *   dst_f32   [co*taps*ci] fp32 (optional),
+ *   dst_fwd   bf16, element (o, r=tap*ci+i) at o*fwd_ld + fwd_col0 + r          (forward GEMM weight)
+ *   dst_dgrad bf16, element at i*dgrad_ld + (taps-1-tap)*co + o                  (transposed, tap-flipped: the
+ *             weight of the data-gradient convolution).   Null destinations are skipped.
+ * The table lives in DEVICE memory. */
+typedef struct hg_pack_entry {
+    const float* src;
+    const float* src2;
+    float* dst_f32;
+    void* dst_fwd;
+    void* dst_dgrad;
+    int32_t co, taps, ci;
+    int32_t fwd_ld, fwd_col0, dgrad_ld;
+} hg_pack_entry;
+int hg_pack_weights(const hg_pack_entry* table_dev, int32_t n_entries, void* stream);
+
+/* torch.optim.RMSprop step (momentum 0, centered False, weight_decay 0; trainer.py:39-41) over flat buffers:
+ * g' = grad_scale*g;  v = alpha*v + (1-alpha)*g'^2;  p -= lr*g'/(sqrt(v)+eps).  count % 4 == 0. */
+int hg_rmsprop_step(float* params, const float* grads, float* square_avg, int64_t count, float lr, float alpha, float eps,
+                    float grad_scale, void* stream);
+
+/* Strided fp32 GEMM for PARAMETER-space algebra only (merged remap weights and their chain rule):
+ * C[i*sci + j*scj] = beta*C + (D ? D[same index] : 0) + sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj]. */
+int hg_small_gemm_f32(float* c, const float* a, const float* b, const float* d, int32_t m, int32_t n, int32_t k,
+                      int32_t sai, int32_t sak, int32_t sbk, int32_t sbj, int32_t sci, int32_t scj, float beta,
+                      void* stream);
 
 #ifdef __cplusplus
 }
