@@ -1,0 +1,730 @@
+"""Training engine: one optimisation step of the stacked hourglass (reference: Trainer._train_epoch,
+src/runner/trainer.py:82-99) as a static plan of sm_100a kernel launches.
+
+  * Parameters live in ONE flat fp32 buffer (gradients and RMSprop state in two more); the model's
+    nn.Parameters are re-pointed to views of it, conv weights in the GEMM-natural [co][kh][kw][ci] order
+    (= torch channels_last), so state_dict()/load_state_dict()/torch.optim keep working while the wgrad
+    kernels write coalesced and one NCCL all-reduce / one RMSprop launch cover the whole network.
+  * Train-mode BatchNorm uses batch statistics, so nothing folds: every BN is a per-channel sum pass
+    (hg_colstats_nhwc) plus one apply pass that materialises Z = relu(bn(a)) -- the next GEMM's operand
+    AND the wgrad operand kept for backward.
+  * Backward per convolution: dgrad = the forward tcgen05 GEMM kernels on transposed (3x3: tap-flipped)
+    bf16 weight copies; wgrad = hg_wgrad_bf16 (MN-major split-K GEMM over pixels); BN backward = two
+    bandwidth passes, the second also adds the residual-path gradients and writes the halo layout the
+    3x3 kernels read.
+  * The plan is built once per (batch, height, width): the forward pass records nodes, the backward
+    pass is emitted by walking them in reverse with gradient buffers recycled in execution order, and
+    the whole step is captured into CUDA graphs.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import HgError
+
+RMSPROP_ALPHA = 0.99      # torch.optim.RMSprop defaults (trainer.py:39-41 passes lr, momentum=0, weight_decay=0)
+RMSPROP_EPS = 1e-8
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+# tests/test_train_plan_cpu.py swaps `ops` for a torch emulation and sets this to exercise the plan's host logic
+# without a GPU; the product path never does (a CPU model raises below).
+_TEST_ALLOW_CPU = False
+_ACT = torch.bfloat16     # activation / GEMM-weight storage type (the same test switches it to fp32 for exact checks)
+
+
+def _pad(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+# ================================================================================================ parameters
+class ParamStore:
+    """Flat fp32 master parameters P, gradients G and RMSprop second moments V; the model's parameters
+    (and their .grad) become views."""
+
+    def __init__(self, model: nn.Module, device):
+        self.device = torch.device(device)
+        named = list(model.named_parameters())
+        self.slots: Dict[str, tuple] = {}
+        off = 0
+        for name, p in named:
+            self.slots[name] = (off, p.numel(), tuple(p.shape))
+            off += _pad(p.numel(), 4)
+        self.count = _pad(off, 4)
+        total = self.count + 256          # tail padding: kernels may read a padded bias vector past the last tensor
+        self.P = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.G = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.V = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.params = dict(named)
+        with torch.no_grad():
+            for name, p in named:
+                view = self.view(self.P, name)
+                view.copy_(p.detach())
+                p.data = view
+                p.grad = self.view(self.G, name)
+
+    def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        off, n, shape = self.slots[name]
+        t = flat[off:off + n]
+        if len(shape) == 4:
+            co, ci, kh, kw = shape
+            return t.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+        return t.view(shape)
+
+    def flat(self, flat: torch.Tensor, name: str, extra: int = 0) -> torch.Tensor:
+        off, n, _ = self.slots[name]
+        return flat[off:off + n + extra]
+
+    def rebind_grads(self):
+        """optimizer.zero_grad(set_to_none=True) drops .grad: point it back at the flat gradient buffer."""
+        for name, p in self.params.items():
+            if p.grad is None or p.grad.data_ptr() != self.G.data_ptr() + self.slots[name][0] * 4:
+                p.grad = self.view(self.G, name)
+
+
+class _T:
+    """An activation in the plan: bf16 NHWC data and (during backward emission) its gradient buffer."""
+    __slots__ = ("data", "grad", "grad_owned")
+
+    def __init__(self, data):
+        self.data = data
+        self.grad = None
+        self.grad_owned = True
+
+
+class _Arena:
+    def __init__(self, device):
+        self.device = device
+        self.free = defaultdict(list)
+        self.total_bytes = 0
+
+    def get(self, shape, dtype=None):
+        dtype = dtype or _ACT
+        key = (tuple(shape), dtype)
+        if self.free[key]:
+            return self.free[key].pop()
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        self.total_bytes += t.numel() * t.element_size()
+        return t
+
+    def put(self, t):
+        self.free[(tuple(t.shape), t.dtype)].append(t)
+
+    def get_halo(self, n, h, w, c):
+        key = ("halo", n, h, w, c)
+        if self.free[key]:
+            return self.free[key].pop()
+        t = ops.halo_padded_buffer(n, h, w, c, self.device)
+        self.total_bytes += t.numel() * 2
+        return t
+
+    def put_halo(self, t, n, h, w, c):
+        self.free[("halo", n, h, w, c)].append(t)
+
+
+# ================================================================================================ records
+class _Conv:
+    """One nn.Conv2d: master slices, gradient slices, bf16 GEMM weights and its weight-pack entries."""
+
+    def __init__(self, eng: "TrainEngine", conv: nn.Conv2d, *, dgrad: bool = True, fwd_ld: Optional[int] = None,
+                 fwd_into=None):
+        st = eng.store
+        wname, bname = eng.pname[id(conv.weight)], eng.pname[id(conv.bias)]
+        co, ci, kh, kw = conv.weight.shape
+        if conv.groups != 1:
+            raise NotImplementedError("mobile=True / skip_mode='concat' (grouped convolutions) are not on the sm_100a "
+                                      "training path yet")
+        self.co, self.ci, self.taps = co, ci, kh * kw
+        self.row_len = self.taps * ci
+        self.w, self.gw = st.flat(st.P, wname), st.flat(st.G, wname)
+        co_pad = _pad(co, 16)
+        self.b = st.flat(st.P, bname, extra=co_pad - co)      # padded view (tail of P is padded)
+        self.gb = st.flat(st.G, bname)
+        dev = st.device
+        if fwd_into is not None:
+            self.wf, col0, ld = fwd_into
+        else:
+            ld = fwd_ld or self.row_len
+            self.wf, col0 = torch.zeros((co_pad, ld), dtype=_ACT, device=dev), 0
+        self.wd = None
+        dgrad_ld = 0
+        if dgrad:
+            dgrad_ld = _pad(self.taps * co, 64)
+            self.wd = torch.zeros((ci, dgrad_ld), dtype=_ACT, device=dev)
+        eng.pack_entries.append(dict(src=self.w, dst_fwd=self.wf, dst_dgrad=self.wd, co=co, taps=self.taps, ci=ci,
+                                     fwd_ld=ld, fwd_col0=col0, dgrad_ld=dgrad_ld))
+
+
+class _Bn:
+    def __init__(self, eng: "TrainEngine", bn: nn.BatchNorm2d):
+        st = eng.store
+        self.c = bn.num_features
+        self.gamma, self.beta = st.flat(st.P, eng.pname[id(bn.weight)]), st.flat(st.P, eng.pname[id(bn.bias)])
+        self.ggamma, self.gbeta = st.flat(st.G, eng.pname[id(bn.weight)]), st.flat(st.G, eng.pname[id(bn.bias)])
+        self.rm, self.rv, self.nbt = bn.running_mean, bn.running_var, bn.num_batches_tracked
+        self.momentum = BN_MOMENTUM if bn.momentum is None else bn.momentum
+        self.eps = bn.eps
+        self.slot = eng.alloc_bn_slot(self.c)     # index into the per-step scratch (bound in bind())
+
+    def bind(self, eng):
+        o = self.slot
+        c = self.c
+        self.sums = eng.stat[o:o + 2 * c]             # forward: sum | sumsq
+        self.bsums = eng.stat[o + 2 * c:o + 4 * c]    # backward: s1 | s2
+        self.saved = eng.saved[o:o + 4 * c]           # mean | invstd | scale | shift
+
+
+class _Block:
+    """One HGBottleneck (src/models/modules.py:6-47): filled in by TrainEngine._block()."""
+    __slots__ = ("cin", "planes", "cout", "bn1", "bn2", "bn3", "c1", "c2", "c3", "ds", "wf3", "b3")
+
+
+class _Remap:
+    """x + fc_(y) + score_(score(y)) (src/models/hourglass.py:86-89) as ONE merged 256->256 GEMM:
+    Wm = W_fc_ + W_score_ W_score, bm = b_fc_ + b_score_ + W_score_ b_score; the chain rule back to the
+    three convolutions' parameters runs in parameter space (hg_small_gemm_f32)."""
+
+    def __init__(self, eng, fc_: nn.Conv2d, score_: nn.Conv2d, score: "_Conv"):
+        st = eng.store
+        dev = st.device
+        n = eng.pname
+        self.ch, self.J = fc_.out_channels, score_.in_channels
+        self.wf_, self.gwf_ = st.flat(st.P, n[id(fc_.weight)]), st.flat(st.G, n[id(fc_.weight)])
+        self.bf_, self.gbf_ = st.flat(st.P, n[id(fc_.bias)]), st.flat(st.G, n[id(fc_.bias)])
+        self.ws_, self.gws_ = st.flat(st.P, n[id(score_.weight)]), st.flat(st.G, n[id(score_.weight)])
+        self.bs_, self.gbs_ = st.flat(st.P, n[id(score_.bias)]), st.flat(st.G, n[id(score_.bias)])
+        self.score = score
+        ch = self.ch
+        self.wm = torch.zeros(ch * ch, dtype=torch.float32, device=dev)
+        self.bm = torch.zeros(ch, dtype=torch.float32, device=dev)
+        self.wf = torch.zeros((ch, ch), dtype=_ACT, device=dev)
+        self.wd = torch.zeros((ch, ch), dtype=_ACT, device=dev)
+        eng.pack_entries.append(dict(src=self.wm, dst_fwd=self.wf, dst_dgrad=self.wd, co=ch, taps=1, ci=ch, fwd_ld=ch,
+                                     fwd_col0=0, dgrad_ld=ch))
+
+    def merge(self, ones):
+        """Launches that build Wm / bm from the current masters (run before the weight pack)."""
+        ch, J, s = self.ch, self.J, self.score
+        ops.small_gemm(self.wm, self.ws_, s.w, self.wf_, ch, ch, J, J, 1, ch, 1, ch, 1)
+        ops.small_gemm(self.bm, self.ws_, s.b, self.bf_, ch, 1, J, J, 1, 1, 0, 1, 0)
+        ops.small_gemm(self.bm, self.bs_, ones, None, ch, 1, 1, 1, 0, 0, 0, 1, 0, beta=1.0)
+
+    def chain(self, ones):
+        """dWm sits in G[fc_.weight] (= dW_fc_), dbm in G[fc_.bias]; spread them to score_ / score."""
+        ch, J, s = self.ch, self.J, self.score
+        # dW_score_[i][j] = sum_k dWm[i][k] W_score[j][k] + dbm[i] b_score[j]
+        ops.small_gemm(self.gws_, self.gwf_, s.w, None, ch, J, ch, ch, 1, 1, ch, J, 1)
+        ops.small_gemm(self.gws_, self.gbf_, s.b, None, ch, J, 1, 1, 0, 0, 1, J, 1, beta=1.0)
+        # dW_score[j][k] += sum_i W_score_[i][j] dWm[i][k] ;  db_score[j] += sum_i W_score_[i][j] dbm[i]
+        ops.small_gemm(s.gw, self.ws_, self.gwf_, None, J, ch, ch, 1, J, ch, 1, ch, 1, beta=1.0)
+        ops.small_gemm(s.gb, self.ws_, self.gbf_, None, J, 1, ch, 1, J, 1, 0, 1, 0, beta=1.0)
+        # db_score_ = dbm
+        ops.small_gemm(self.gbs_, self.gbf_, ones, None, ch, 1, 1, 1, 0, 0, 0, 1, 0)
+
+
+# ================================================================================================ plan
+class TrainPlan:
+    def __init__(self, eng: "TrainEngine", n: int, h: int, w: int):
+        self.eng = eng
+        self.n, self.h, self.w = n, h, w
+        dev = eng.device
+        S, J = eng.num_stacks, eng.num_classes
+        hh, ww = h // 4, w // 4
+        self.input = torch.zeros((n, 3, h, w), dtype=torch.float32, device=dev)
+        self.target = torch.zeros((n, J, hh, ww), dtype=torch.float32, device=dev)
+        self.target_weight = torch.ones((n, J), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.outputs = [torch.empty((n, J, hh, ww), dtype=torch.float32, device=dev) for _ in range(S)]
+        self.dheat = [torch.zeros((n, J, hh, ww), dtype=torch.float32, device=dev) for _ in range(S)]
+        self.pre: List[Callable] = []
+        self.fwd: List[Callable] = []
+        self.bwd: List[Callable] = []
+        self.post: List[Callable] = []
+        self.meta_fwd: List[str] = []
+        self.meta_bwd: List[str] = []
+        self.nodes: List[dict] = []
+        self.grad_scale = 1.0          # 1/world_size: the sum over ranks is the global-batch mean
+        self.use_target_weight = True
+        self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        self.fwd_bytes = 0
+        self.bwd_arena_bytes = 0
+
+    # ---- launch lists
+    def _loss_launches(self):
+        def run():
+            self.loss.zero_()
+            ops.jmse_loss_into(self.outputs, self.dheat, self.target, self.target_weight if self.use_target_weight else None,
+                               self.loss, grad_scale=self.grad_scale)
+        return [run]
+
+    def launches(self, which: str) -> List[Callable]:
+        if which == "fwd":
+            return self.pre + self.fwd
+        if which == "bwd":
+            return self.bwd + self.post
+        if which == "step":
+            return self.pre + self.fwd + self._loss_launches() + self.bwd + self.post
+        raise KeyError(which)
+
+    def run(self, which: str, use_graph: bool = True):
+        if use_graph:
+            g = self.graphs.get(which)
+            if g is None:
+                g = self._capture(which)
+            g.replay()
+        else:
+            for fn in self.launches(which):
+                fn()
+
+    def _capture(self, which: str):
+        # PLAIN capture of the closures; the caller must have run the list eagerly once before (module loading,
+        # shared-memory opt-in) -- TrainEngine.plan_for() does that on a scratch copy of the BN statistics.
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for fn in self.launches(which):
+                fn()
+        self.graphs[which] = g
+        return g
+
+
+class TrainEngine:
+    def __init__(self, model: nn.Module, device=None):
+        device = torch.device(device or next(model.parameters()).device)
+        if device.type != "cuda" and not _TEST_ALLOW_CPU:
+            raise HgError("TrainEngine needs a CUDA device (no CPU fallback)")
+        self.device = device
+        self.model = model
+        for b in model.buffers():
+            if b.device != device:
+                raise HgError("move the model to the device (model.to('cuda')) before training")
+        self.store = ParamStore(model, device)
+        self.pname = {id(p): n for n, p in model.named_parameters()}
+        self.pack_entries: List[dict] = []
+        self._bn_floats = 0
+        self._bns: List[_Bn] = []
+        self.num_stacks = model.num_stacks
+        self.num_classes = model.score[0].out_channels
+        self.depth = 4
+
+        self.stem = _Conv(self, model.conv1, dgrad=False, fwd_ld=192)
+        self.stem_bn = self._bn(model.bn1)
+        self.layer1 = [self._block(m) for m in model.layer1]
+        self.layer2 = [self._block(m) for m in model.layer2]
+        self.layer3 = [self._block(m) for m in model.layer3]
+        self.hg, self.res, self.fc, self.score, self.remap = [], [], [], [], []
+        for i in range(self.num_stacks):
+            levels = []
+            for d in range(self.depth):
+                levels.append([[self._block(m) for m in chain] for chain in model.hg[i].hg[d]])
+            self.hg.append(levels)
+            self.res.append([self._block(m) for m in model.res[i]])
+            self.fc.append((_Conv(self, model.fc[i][0]), self._bn(model.fc[i][1])))
+            self.score.append(_Conv(self, model.score[i]))
+            if i < self.num_stacks - 1:
+                self.remap.append(_Remap(self, model.fc_[i], model.score_[i], self.score[i]))
+        # per-step scratch: BN forward/backward sums (zeroed every step) and saved statistics
+        self.stat = torch.zeros(self._bn_floats, dtype=torch.float32, device=device)
+        self.saved = torch.zeros(self._bn_floats, dtype=torch.float32, device=device)
+        for b in self._bns:
+            b.bind(self)
+        self.ones = torch.ones(4, dtype=torch.float32, device=device)
+        self.pack_table = ops.make_pack_table(self.pack_entries, device)
+        self.plans: Dict[tuple, TrainPlan] = {}
+        self.steps = 0
+
+    # ------------------------------------------------------------------ construction helpers
+    def alloc_bn_slot(self, c: int) -> int:
+        o = self._bn_floats
+        self._bn_floats += 4 * c
+        return o
+
+    def _bn(self, m):
+        b = _Bn(self, m)
+        self._bns.append(b)
+        return b
+
+    def _block(self, m):
+        blk = _Block()
+        blk.cin, blk.planes, blk.cout = m.conv1.in_channels, m.conv1.out_channels, m.conv3.out_channels
+        blk.bn1, blk.bn2, blk.bn3 = self._bn(m.bn1), self._bn(m.bn2), self._bn(m.bn3)
+        blk.c1, blk.c2 = _Conv(self, m.conv1), _Conv(self, m.conv2)
+        blk.ds = None
+        if m.downsample is not None:
+            dev = self.device
+            k = blk.planes + blk.cin
+            blk.wf3 = torch.zeros((blk.cout, k), dtype=_ACT, device=dev)
+            blk.c3 = _Conv(self, m.conv3, fwd_into=(blk.wf3, 0, k))
+            blk.ds = _Conv(self, m.downsample[0], fwd_into=(blk.wf3, blk.planes, k))
+            blk.b3 = torch.zeros(blk.cout, dtype=torch.float32, device=dev)
+            self.pack_entries.append(dict(src=blk.c3.b[:blk.cout], src2=blk.ds.b[:blk.cout], dst_f32=blk.b3, co=blk.cout,
+                                          taps=1, ci=1))
+        else:
+            blk.c3 = _Conv(self, m.conv3)
+            blk.wf3 = blk.c3.wf
+            blk.b3 = blk.c3.b
+        return blk
+
+    # ------------------------------------------------------------------ plan construction
+    def build_plan(self, n: int, h: int, w: int) -> TrainPlan:
+        if h % 64 or w % 64:
+            raise HgError(f"input {h}x{w}: height and width must be multiples of 64")
+        plan = TrainPlan(self, n, h, w)
+        dev = self.device
+        F, nodes = plan.fwd, plan.nodes
+        fwd_bytes = [0]
+
+        def new(shape, dtype=None):
+            dtype = dtype or _ACT
+            t = torch.empty(shape, dtype=dtype, device=dev)
+            fwd_bytes[0] += t.numel() * t.element_size()
+            return t
+
+        def new_halo(nn_, hh_, ww_, c):
+            t = ops.halo_padded_buffer(nn_, hh_, ww_, c, dev)
+            fwd_bytes[0] += t.numel() * 2
+            return t
+
+        def bn_fwd(bn: _Bn, x, out, halo=False):
+            F.append(lambda: ops.colstats(x, bn.sums[:bn.c], bn.sums[bn.c:]))
+            F.append(lambda: ops.bn_train_fwd(x, bn.sums, bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, bn.saved, out, halo=halo,
+                                              relu=True, eps=bn.eps, momentum=bn.momentum))
+
+        def block(blk: _Block, x: _T, up_low: Optional[_T] = None) -> _T:
+            nb, hh_, ww_, cin = x.data.shape
+            pl = blk.planes
+            z1 = new((nb, hh_, ww_, cin))
+            a1 = new((nb, hh_, ww_, pl))
+            z2h = new_halo(nb, hh_, ww_, pl)
+            a2 = new((nb, hh_, ww_, pl))
+            z3 = new((nb, hh_, ww_, pl))
+            y = _T(new((nb, hh_, ww_, blk.cout)))
+            xd = x.data
+            bn_fwd(blk.bn1, xd, z1)
+            F.append(lambda: ops.conv_nhwc(z1, blk.c1.wf, blk.c1.b, ksize=1, cout=pl, out=a1))
+            bn_fwd(blk.bn2, a1, z2h, halo=True)
+            F.append(lambda: ops.conv3x3_halo(z2h, blk.c2.wf, blk.c2.b, n=nb, h=hh_, w=ww_, cin=pl, cout=pl, out=a2))
+            bn_fwd(blk.bn3, a2, z3)
+            lowd = up_low.data if up_low is not None else None
+            if blk.ds is not None:
+                F.append(lambda: ops.conv_nhwc(z3, blk.wf3, blk.b3, ksize=1, cout=blk.cout, x2=xd, up_low=lowd, out=y.data))
+            else:
+                F.append(lambda: ops.conv_nhwc(z3, blk.wf3, blk.b3, ksize=1, cout=blk.cout, residual=xd, up_low=lowd,
+                                               out=y.data))
+            nodes.append(dict(kind="block", blk=blk, x=x, y=y, up_low=up_low, z1=z1, a1=a1, z2h=z2h, a2=a2, z3=z3))
+            return y
+
+        def chain(blocks, x, up_low=None):
+            cur = x
+            for i, blk in enumerate(blocks):
+                cur = block(blk, cur, up_low if i == len(blocks) - 1 else None)
+            return cur
+
+        def pool(x: _T) -> _T:
+            nb, hh_, ww_, c = x.data.shape
+            p = _T(new((nb, hh_ // 2, ww_ // 2, c)))
+            F.append(lambda: ops.maxpool2x2(x.data, p.data))
+            nodes.append(dict(kind="pool", x=x, y=p))
+            return p
+
+        def hourglass(levels, d, x: _T) -> _T:
+            p = pool(x)
+            low1 = chain(levels[d][1], p)
+            low2 = hourglass(levels, d - 1, low1) if d > 0 else chain(levels[0][3], low1)
+            low3 = chain(levels[d][2], low2)
+            return chain(levels[d][0], x, up_low=low3)
+
+        # ---- stem: im2col rows (kept: they are the stem's wgrad operand) -> GEMM -> BN+ReLU
+        rows = new((n, h // 2, w // 2, 192))
+        a0 = new((n, h // 2, w // 2, 64))
+        s0 = _T(new((n, h // 2, w // 2, 64)))
+        F.append(lambda: ops.stem_im2col(plan.input, out=rows))
+        F.append(lambda: ops.conv_nhwc(rows, self.stem.wf, self.stem.b, ksize=1, cout=64, out=a0))
+        bn_fwd(self.stem_bn, a0, s0.data)
+        nodes.append(dict(kind="stem", rows=rows, a0=a0, y=s0))
+        l1 = chain(self.layer1, s0)
+        p1 = pool(l1)
+        l2 = chain(self.layer2, p1)
+        x = chain(self.layer3, l2)
+        J = self.num_classes
+        for i in range(self.num_stacks):
+            y = hourglass(self.hg[i], self.depth - 1, x)
+            y = chain(self.res[i], y)
+            fcc, fcb = self.fc[i]
+            nb, hh_, ww_, ch = y.data.shape
+            afc = new((nb, hh_, ww_, ch))
+            y2 = _T(new((nb, hh_, ww_, ch)))
+            F.append(lambda y=y, afc=afc, fcc=fcc: ops.conv_nhwc(y.data, fcc.wf, fcc.b, ksize=1, cout=ch, out=afc))
+            bn_fwd(fcb, afc, y2.data)
+            nodes.append(dict(kind="fc", conv=fcc, bn=fcb, x=y, a=afc, y=y2))
+            sc = self.score[i]
+            F.append(lambda y2=y2, sc=sc, i=i: ops.conv_nhwc(y2.data, sc.wf, sc.b, ksize=1, cout=J, heads=True,
+                                                             out_nchw_f32=plan.outputs[i]))
+            nodes.append(dict(kind="score", conv=sc, x=y2, idx=i))
+            if i < self.num_stacks - 1:
+                rm = self.remap[i]
+                xn = _T(new((nb, hh_, ww_, ch)))
+                F.append(lambda y2=y2, rm=rm, x=x, xn=xn: ops.conv_nhwc(y2.data, rm.wf, rm.bm, ksize=1, cout=ch,
+                                                                       residual=x.data, out=xn.data))
+                nodes.append(dict(kind="remap", rm=rm, x=x, y2=y2, y=xn))
+                x = xn
+        plan.fwd_bytes = fwd_bytes[0]
+
+        # ---- pre: zero the per-step scratch, merge the remap weights, pack every GEMM weight (one launch)
+        plan.pre.append(lambda: self.stat.zero_())
+        for rm in self.remap:
+            plan.pre.append(lambda rm=rm: rm.merge(self.ones))
+        plan.pre.append(lambda: ops.pack_weights(self.pack_table, len(self.pack_entries)))
+
+        self._emit_backward(plan)
+        for rm in self.remap:
+            plan.post.append(lambda rm=rm: rm.chain(self.ones))
+        return plan
+
+    # ------------------------------------------------------------------ backward emission (reverse node order)
+    def _emit_backward(self, plan: TrainPlan):
+        dev = self.device
+        B = plan.bwd
+        arena = _Arena(dev)
+        G = self.store.G
+        B.append(lambda: G.zero_())
+
+        def release(t: _T):
+            if t.grad is not None and t.grad_owned:
+                arena.put(t.grad)
+            t.grad = None
+
+        def dgrad1x1(g, wd, cout, out, residual=None):
+            B.append(lambda: ops.conv_nhwc(g, wd, None, ksize=1, cout=cout, residual=residual, out=out))
+
+        def bn_bwd(bn: _Bn, dz, xdata, out, *, add1=None, add2=None, halo=False):
+            B.append(lambda: ops.bn_bwd_reduce(dz, xdata, bn.saved, bn.bsums))
+            B.append(lambda: ops.bn_bwd_apply(dz, xdata, bn.saved, bn.bsums, out, add1=add1, add2=add2, dgamma=bn.ggamma,
+                                              dbeta=bn.gbeta, halo=halo))
+
+        for node in reversed(plan.nodes):
+            kind = node["kind"]
+            if kind == "block":
+                blk, x, y, low = node["blk"], node["x"], node["y"], node["up_low"]
+                gy = y.grad
+                if gy is None:
+                    raise HgError("internal: block output without a gradient")
+                nb, hh_, ww_, cin = x.data.shape
+                pl, cout = blk.planes, blk.cout
+                if low is not None:
+                    acc = low.grad is not None
+                    if not acc:
+                        low.grad = arena.get(low.data.shape)
+                    B.append(lambda gy=gy, lg=low.grad, acc=acc: ops.sumpool2x2(gy, lg, accumulate=acc))
+                B.append(lambda gy=gy, blk=blk: ops.colstats(gy, blk.c3.gb))
+                B.append(lambda gy=gy, blk=blk, z3=node["z3"]: ops.wgrad(gy, z3, blk.c3.gw))
+                if blk.ds is not None:
+                    B.append(lambda gy=gy, blk=blk: ops.colstats(gy, blk.ds.gb))
+                    B.append(lambda gy=gy, blk=blk, xd=x.data: ops.wgrad(gy, xd, blk.ds.gw))
+                dz3 = arena.get((nb, hh_, ww_, pl))
+                dgrad1x1(gy, blk.c3.wd, pl, dz3)
+                da2h = arena.get_halo(nb, hh_, ww_, pl)
+                bn_bwd(blk.bn3, dz3, node["a2"], da2h, halo=True)
+                arena.put(dz3)
+                B.append(lambda da2h=da2h, z2h=node["z2h"], blk=blk, P=ww_ + 1, pl=pl:
+                         ops.wgrad(da2h.view(-1, pl), z2h.view(-1, pl), blk.c2.gw, taps=9, halo_pitch=P))
+                dz2 = arena.get((nb, hh_, ww_, pl))
+                B.append(lambda da2h=da2h, blk=blk, dz2=dz2, nb=nb, hh_=hh_, ww_=ww_, pl=pl:
+                         ops.conv3x3_halo(da2h, blk.c2.wd, None, n=nb, h=hh_, w=ww_, cin=pl, cout=pl, out=dz2))
+                arena.put_halo(da2h, nb, hh_, ww_, pl)
+                da1 = arena.get((nb, hh_, ww_, pl))
+                bn_bwd(blk.bn2, dz2, node["a1"], da1)
+                arena.put(dz2)
+                B.append(lambda da1=da1, z1=node["z1"], blk=blk: ops.wgrad(da1, z1, blk.c1.gw))
+                dz1 = arena.get((nb, hh_, ww_, cin))
+                dgrad1x1(da1, blk.c1.wd, cin, dz1)
+                arena.put(da1)
+                # gradient of the block input: BN1 backward + the residual path (+ whatever x already collected)
+                if blk.ds is not None:
+                    r = arena.get((nb, hh_, ww_, cin))
+                    dgrad1x1(gy, blk.ds.wd, cin, r)
+                    if x.grad is None:
+                        x.grad = arena.get((nb, hh_, ww_, cin))
+                        bn_bwd(blk.bn1, dz1, x.data, x.grad, add1=r)
+                    else:
+                        bn_bwd(blk.bn1, dz1, x.data, x.grad, add1=r, add2=x.grad)
+                    arena.put(r)
+                    release(y)
+                else:
+                    if x.grad is None:
+                        # the identity path hands y's gradient buffer on to x; BN1's contribution is added in place
+                        x.grad, x.grad_owned = gy, y.grad_owned
+                        y.grad = None
+                        bn_bwd(blk.bn1, dz1, x.data, x.grad, add1=gy)
+                    else:
+                        bn_bwd(blk.bn1, dz1, x.data, x.grad, add1=gy, add2=x.grad)
+                        release(y)
+                arena.put(dz1)
+            elif kind == "pool":
+                x, y = node["x"], node["y"]
+                acc = x.grad is not None
+                if not acc:
+                    x.grad = arena.get(x.data.shape)
+                B.append(lambda x=x.data, gy=y.grad, gx=x.grad, acc=acc: ops.maxpool2x2_bwd(x, gy, gx, acc))
+                release(y)
+            elif kind == "remap":
+                rm, x, y2, y = node["rm"], node["x"], node["y2"], node["y"]
+                gy = y.grad
+                B.append(lambda gy=gy, rm=rm: ops.colstats(gy, rm.gbf_))
+                B.append(lambda gy=gy, rm=rm, y2=y2.data: ops.wgrad(gy, y2, rm.gwf_))
+                assert y2.grad is None
+                y2.grad = arena.get(y2.data.shape)
+                dgrad1x1(gy, rm.wd, rm.ch, y2.grad)
+                assert x.grad is None
+                x.grad, x.grad_owned = gy, y.grad_owned      # identity: x inherits the buffer
+                y.grad = None
+            elif kind == "score":
+                sc, x, i = node["conv"], node["x"], node["idx"]
+                nb, hh_, ww_, ch = x.data.shape
+                J = self.num_classes
+                dhp = arena.get((nb, hh_, ww_, 64))
+                B.append(lambda i=i, dhp=dhp: ops.nchw_to_nhwc_bf16_pad(plan.dheat[i], dhp))
+                B.append(lambda dhp=dhp, sc=sc, J=J: ops.colstats(dhp, sc.gb, c_valid=J))
+                B.append(lambda dhp=dhp, sc=sc, xd=x.data, J=J: ops.wgrad(dhp, xd, sc.gw, co_valid=J))
+                if x.grad is None:
+                    x.grad = arena.get(x.data.shape)
+                    dgrad1x1(dhp, sc.wd, ch, x.grad)
+                else:
+                    dgrad1x1(dhp, sc.wd, ch, x.grad, residual=x.grad)
+                arena.put(dhp)
+            elif kind == "fc":
+                cv, bn, x, y = node["conv"], node["bn"], node["x"], node["y"]
+                da = arena.get(y.data.shape)
+                bn_bwd(bn, y.grad, node["a"], da)
+                release(y)
+                B.append(lambda da=da, xd=x.data, cv=cv: ops.wgrad(da, xd, cv.gw))
+                assert x.grad is None
+                x.grad = arena.get(x.data.shape)
+                dgrad1x1(da, cv.wd, cv.ci, x.grad)
+                arena.put(da)
+            elif kind == "stem":
+                y = node["y"]
+                da0 = arena.get(y.data.shape)
+                bn_bwd(self.stem_bn, y.grad, node["a0"], da0)
+                release(y)
+                B.append(lambda da0=da0, rows=node["rows"]: ops.wgrad(da0, rows, self.stem.gw, ci_valid=147, ld=147,
+                                                                      tap_stride=147))
+                arena.put(da0)
+            else:
+                raise HgError(f"internal: unknown node kind {kind}")
+        plan.bwd_arena_bytes = arena.total_bytes
+
+    # ------------------------------------------------------------------ public
+    def plan_for(self, n: int, h: int, w: int) -> TrainPlan:
+        key = (n, h, w)
+        p = self.plans.get(key)
+        if p is None:
+            p = self.build_plan(n, h, w)
+            if self.device.type != "cuda":          # host-logic tests only (_TEST_ALLOW_CPU)
+                self.plans[key] = p
+                return p
+            # one eager pass on a side stream with the BN running statistics preserved: loads every kernel and opts
+            # in to large shared memory before any graph capture
+            bufs = [(b.rm, b.rv, b.nbt) for b in self._bns]
+            keep = [(a.clone(), b.clone(), c.clone()) for a, b, c in bufs]
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                for fn in p.launches("step"):
+                    fn()
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            torch.cuda.synchronize(self.device)
+            ops.check_err_word(self.device)
+            for (a, b, c), (ka, kb, kc) in zip(bufs, keep):
+                a.copy_(ka)
+                b.copy_(kb)
+                c.copy_(kc)
+            self.plans[key] = p
+        return p
+
+    def rmsprop(self, lr: float, alpha: float = RMSPROP_ALPHA, eps: float = RMSPROP_EPS):
+        st = self.store
+        ops.rmsprop_step(st.P[:st.count], st.G[:st.count], st.V[:st.count], lr, alpha, eps)
+        self.mark_updated()
+
+    def mark_updated(self):
+        self.steps += 1
+        self.model._weights_epoch = getattr(self.model, "_weights_epoch", 0) + 1
+
+    def train_step(self, x: torch.Tensor, target: torch.Tensor, target_weight: Optional[torch.Tensor], lr: float, *,
+                   use_graph: bool = True, world_size: int = 1, all_reduce: Optional[Callable] = None) -> torch.Tensor:
+        """One fused step: forward, JointsMSE loss, backward, (all-reduce,) RMSprop.  Returns the plan's loss
+        tensor (device, fp32 [1]; the LOCAL loss already scaled by 1/world_size)."""
+        n, _, h, w = x.shape
+        plan = self.plan_for(n, h, w)
+        plan.input.copy_(x, non_blocking=True)
+        plan.target.copy_(target, non_blocking=True)
+        if target_weight is not None:
+            plan.target_weight.copy_(target_weight.reshape(n, -1), non_blocking=True)
+        gs = 1.0 / world_size
+        if plan.grad_scale != gs or plan.use_target_weight != (target_weight is not None):
+            plan.grad_scale, plan.use_target_weight = gs, target_weight is not None
+            plan.graphs.clear()
+        plan.run("step", use_graph)
+        if all_reduce is not None:
+            all_reduce(self.store.G[:self.store.count])
+        self.rmsprop(lr)
+        return plan.loss
+
+
+# ================================================================================================ autograd drop-in
+class _TrainFn(torch.autograd.Function):
+    """model(x) in train mode under the reference's own loop (criterion(...).backward(); optimizer.step()):
+    forward runs the plan's forward graph; backward feeds the heat-map gradients to the backward graph, which
+    leaves every parameter gradient in the flat buffer the parameters' .grad views alias."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, eng: TrainEngine, use_graph: bool):
+        n, _, h, w = x.shape
+        plan = eng.plan_for(n, h, w)
+        plan.input.copy_(x, non_blocking=True)
+        plan.run("fwd", use_graph)
+        ctx.plan, ctx.eng, ctx.use_graph = plan, eng, use_graph
+        return tuple(o.clone() for o in plan.outputs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        plan, eng = ctx.plan, ctx.eng
+        for dst, g in zip(plan.dheat, grads):
+            if g is None:
+                dst.zero_()
+            else:
+                dst.copy_(g, non_blocking=True)
+        plan.run("bwd", ctx.use_graph)
+        eng.store.rebind_grads()
+        return None, None, None, None
+
+
+def train_engine(model: nn.Module) -> TrainEngine:
+    eng = getattr(model, "_train_engine", None)
+    if eng is None:
+        eng = TrainEngine(model)
+        model._train_engine = eng
+    return eng
+
+
+def training_forward(model: nn.Module, x: torch.Tensor):
+    dev = next(model.parameters()).device
+    if dev.type != "cuda" and not _TEST_ALLOW_CPU:
+        raise RuntimeError("HourglassNet (B200 build) trains on CUDA only: there is no CPU fallback; "
+                           "move the model with .to('cuda')")
+    eng = train_engine(model)
+    x = x.to(device=dev, dtype=torch.float32).contiguous()
+    if not torch.is_grad_enabled():
+        n, _, h, w = x.shape
+        plan = eng.plan_for(n, h, w)
+        plan.input.copy_(x, non_blocking=True)
+        plan.run("fwd", model.use_cuda_graph)
+        return [o.clone() for o in plan.outputs]
+    anchor = model.conv1.weight          # any leaf that requires grad: makes autograd call backward()
+    model._weights_epoch = getattr(model, "_weights_epoch", 0) + 1     # an optimizer step will follow
+    return list(_TrainFn.apply(x, anchor, eng, model.use_cuda_graph))

@@ -83,8 +83,9 @@ class HourglassNet(nn.Module):
     # ------------------------------------------------------------------ sm_100a execution
     def _weights_key(self, device):
         # in-place updates (optimizer.step, load_state_dict's copy_) bump tensor._version
+        # (the fused training step updates parameters through raw pointers and bumps _weights_epoch instead)
         return (str(device), sum(int(t._version) for t in self.state_dict(keep_vars=True).values()),
-                tuple(id(p) for p in self.parameters()))
+                tuple(id(p) for p in self.parameters()), getattr(self, "_weights_epoch", 0))
 
     def engine(self, device=None):
         """The folded-weight inference engine for the current parameters (rebuilt when they change)."""
