@@ -9,6 +9,10 @@ Metric: images/sec (original images, whole job over all GPUs).  One "step" = one
   python bench.py --impl reference ...                           the reference algorithm on the host CPUs
                                                                 (oracle port: /root/reference does not travel)
 
+  python bench.py --workload train ...                            C3: 8-stack training step, batch 32 per GPU, JointsMSE
+                                                                over all stacks, RMSprop; N>1 = data parallel with one
+                                                                NCCL all-reduce of the flat gradient buffer per step
+
 N>1 is launched by torchrun (one rank per GPU); inference shards by batch with no collective, so the only
 torch.distributed traffic is the timing barrier / max-over-ranks.
 """
@@ -162,6 +166,183 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ training workload (C3)
+TRAIN_GFLOP_PER_IMAGE = 3 * FWD_GFLOP_PER_IMAGE      # fwd + dgrad + wgrad
+TRAIN_METRIC = "images/sec 8-stack HG 256x256 train"
+TRAIN_WORKLOAD = "C3: 8-stack hourglass MPII training, intermediate-supervision JointsMSELoss, RMSprop, batch 32/GPU, bf16"
+
+
+def cpu_train_rate(n_images: int, steps: int):
+    """The reference's training step (oracle port: fp32 torch autograd on the host cores + RMSprop) on a bounded sample."""
+    import torch
+    from oracle.hourglass_oracle import make_state_dict
+    from oracle import train_oracle as T
+    from oracle.make_golden_inputs import train_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_state_dict(num_stacks=8, num_blocks=1, num_classes=16, seed=0)
+    batches = train_inputs(1, n_images, 16, 256, 256, steps + 1)
+    state = {}
+    T.train_steps(sd, batches[:1], 2.5e-4)
+    t0 = time.perf_counter()
+    for b in batches[1:]:
+        _, _, grads = T.forward_backward(sd, *b)
+        T.rmsprop_update(sd, grads, state, 2.5e-4)
+    dt = (time.perf_counter() - t0) / steps
+    return n_images / dt, dt * 1e3, cores
+
+
+def run_train(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_img, steps = 2, max(1, min(args.steps, 3))
+        rate, ms, cores = cpu_train_rate(n_img, steps)
+        sample = f"{n_img} images/step (of the 32-image batch), 8-stack train step fwd+bwd+RMSprop, fp32, {cores} threads"
+        print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+                          "steps": steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": TRAIN_WORKLOAD, "sample": sample},
+                          "cpu_baseline": {"value": rate, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sm_100a path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    from hgb200 import lib, ops
+    from hgb200.train import train_engine
+    from src.models import hg
+    lib.check(lib.hg_check_device(), "hg_check_device")
+    steps, warmup = args.steps, max(3, args.warmup)
+    B = args.batch if args.batch != 128 else 32
+    J, H, W, lr = 16, 256, 256, 2.5e-4
+    torch.manual_seed(0)                                     # identical initial weights on every rank
+    model = hg(num_stacks=8, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum", out_res=64).to(device).train()
+    eng = train_engine(model)
+    rng = np.random.RandomState(100 + rank)
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    host_x = [torch.randn(B, 3, H, W, generator=g).pin_memory() for _ in range(2)]
+    joints = np.zeros((B, J, 3))
+    joints[..., 0], joints[..., 1] = rng.uniform(0, W, (B, J)), rng.uniform(0, H, (B, J))
+    vis = (rng.rand(B, J, 1) < 0.8).astype(np.float64).repeat(3, 2)
+    host_j, host_v = torch.from_numpy(joints).pin_memory(), torch.from_numpy(vis).pin_memory()
+    x_dev, j_dev, v_dev = host_x[0].to(device), host_j.to(device), host_v.to(device)
+    reduce_fn = (lambda flat: dist.all_reduce(flat, op=dist.ReduceOp.SUM)) if world > 1 else None
+
+    def step(x, jt, vs):
+        mu, wt = ops.joint_centers(jt, vs, (W // 4, H // 4), (W, H), 1)          # on-device Gaussian targets (A7)
+        tgt = ops.gaussian_target(mu, wt, (W // 4, H // 4), 1)
+        return eng.train_step(x, tgt, wt, lr, world_size=world, all_reduce=reduce_fn)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    for _ in range(warmup):
+        loss = step(x_dev, j_dev, v_dev)
+    barrier()
+    ops.check_err_word(device)
+    loss0 = float(loss)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        loss = step(x_dev, j_dev, v_dev)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / steps
+    value = world * B / (ms_step * 1e-3)
+    ops.check_err_word(device)
+    loss1 = float(loss)
+    # ---- end to end: pinned host images + joints -> H2D, step, loss read back every step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        xd = host_x[i & 1].to(device, non_blocking=True)
+        jd, vd = host_j.to(device, non_blocking=True), host_v.to(device, non_blocking=True)
+        lv = float(step(xd, jd, vd).item())
+    torch.cuda.synchronize(device)
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * steps / float(te.item())
+    # ---- roofline of the dominant kernel class
+    hbm_peak, tf_burst, tf_sustained, peak_src = load_peaks()
+    plan = eng.plans[(B, H, W)]
+    per = plan.profile(iters=2)
+    classes = {}
+    for ms, meta in zip(per, plan.meta):
+        c = classes.setdefault(meta["op"], dict(ms=0.0, n=0, flops=meta["flops"], bytes=meta["bytes"], kind=meta["kind"]))
+        c["ms"] += ms
+        c["n"] += 1
+    total_ms = sum(per)
+    top_name, top = max(classes.items(), key=lambda kv: kv[1]["ms"])
+    avg_ms = top["ms"] / top["n"]
+    if top["kind"] == "conv" and top["flops"] / max(top["bytes"], 1) > tf_sustained * 1e12 / (hbm_peak * 1e9):
+        roofline = {"bound": "tensor", "achieved": top["flops"] / (avg_ms * 1e-3) / 1e12, "peak": tf_sustained, "unit": "TFLOP/s"}
+    else:
+        roofline = {"bound": "hbm", "achieved": top["bytes"] / (avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
+    roofline.update(frac=roofline["achieved"] / roofline["peak"], traffic=None, kernel=top_name, launches_per_step=top["n"],
+                    share_of_step=top["ms"] / total_ms,
+                    peak_source=f"{peak_src} (sustained bf16 / copy bandwidth, MEASURED_PEAKS.json)")
+    if args.breakdown and rank == 0:
+        with open(args.breakdown, "w") as f:
+            f.write(f"# train step, per-kernel-class device time, eager replay with CUDA events, batch {B}; total {total_ms:.3f} ms; "
+                    f"graph step {ms_step:.3f} ms\n")
+            f.write("class,launches,total_ms,avg_ms,share,TFLOP/s,GB/s\n")
+            for name, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
+                a = c["ms"] / c["n"]
+                f.write(f"{name},{c['n']},{c['ms']:.4f},{a:.4f},{c['ms']/total_ms:.4f},"
+                        f"{c['flops']/(a*1e-3)/1e12:.1f},{c['bytes']/(a*1e-3)/1e9:.0f}\n")
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, ms, cores = cpu_train_rate(2, 2)
+        cpu = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "2 images/step, 2 steps: oracle port of the reference train step (fp32 torch CPU autograd + RMSprop)"}
+    flops_per_step = TRAIN_GFLOP_PER_IMAGE * 1e9 * B
+    line = {
+        "metric": TRAIN_METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": TRAIN_WORKLOAD, "images_per_gpu_per_step": B,
+                   "parallelism": f"data parallel x{world}, one NCCL all-reduce of the flat fp32 gradient buffer per step",
+                   "l2": "working set (>9 GB of saved activations per step) far exceeds the 126 MB L2; no flush needed",
+                   "weights": "random init (torch default)", "loss_first_last": [loss0, loss1]},
+        "tensor_tflops": flops_per_step / (ms_step * 1e-3) / 1e12,
+        "tensor_frac_of_measured_peak": flops_per_step / (ms_step * 1e-3) / 1e12 / tf_sustained,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4 + 2 * B * J * 3 * 8,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": (plan.num_kernel_launches + 3) * steps,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -172,7 +353,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-kernel-class time breakdown to this file")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer = C2 flip-test inference (headline); train = C3 training step")
     args = ap.parse_args()
+    if args.workload == "train":
+        run_train(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

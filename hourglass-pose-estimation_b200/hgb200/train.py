@@ -227,6 +227,67 @@ class _Remap:
         ops.small_gemm(self.gbs_, self.gbf_, ones, None, ch, 1, 1, 1, 0, 0, 0, 1, 0)
 
 
+# ================================================================================================ launch accounting
+def _nbytes(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if torch.is_tensor(t))
+
+
+def _describe(name, a, k):
+    """Algorithmic flops / bytes of one library call, from its arguments (bench.py's roofline accounting)."""
+    flops, nbytes, tag = 0.0, 0, name
+    if name == "conv_nhwc":
+        x, wt = a[0], a[1]
+        pixels = x.numel() // x.shape[-1]
+        cout = k["cout"]
+        flops = 2.0 * pixels * wt.shape[1] * cout
+        out = k.get("out") if k.get("out") is not None else k.get("out_nchw_f32")
+        nbytes = _nbytes(x, wt, k.get("x2"), k.get("residual"), k.get("up_low"), out)
+        tag = f"conv1x1_k{wt.shape[1]}_n{cout}_{x.shape[1]}x{x.shape[2]}" + ("_res" if k.get("residual") is not None else "") \
+            + ("_up" if k.get("up_low") is not None else "") + ("_x2" if k.get("x2") is not None else "")
+    elif name == "conv3x3_halo":
+        wt = a[1]
+        pixels = k["n"] * k["h"] * k["w"]
+        flops = 2.0 * pixels * 9 * k["cin"] * k["cout"]
+        nbytes = pixels * (k["cin"] + k["cout"]) * 2 + _nbytes(wt)
+        tag = f"conv3x3h_k{9 * k['cin']}_n{k['cout']}_{k['h']}x{k['w']}"
+    elif name == "wgrad":
+        dout, z, dw = a[0], a[1], a[2]
+        taps = k.get("taps", 1)
+        rows = dout.numel() // dout.shape[-1]
+        co = k.get("co_valid") or dout.shape[-1]
+        flops = 2.0 * rows * co * z.shape[-1] * taps
+        nbytes = _nbytes(dout, z) + co * z.shape[-1] * taps * 4
+        tag = f"wgrad_co{dout.shape[-1]}_ci{z.shape[-1]}_t{taps}_rows{rows}"
+    elif name in ("colstats", "bn_train_fwd", "bn_bwd_reduce", "bn_bwd_apply", "maxpool2x2", "maxpool2x2_bwd", "sumpool2x2",
+                  "add_inplace", "nchw_to_nhwc_bf16_pad", "stem_im2col"):
+        big = [t for t in list(a) + list(k.values()) if torch.is_tensor(t) and t.numel() > 4096]
+        nbytes = _nbytes(*big)
+        ref = big[0] if big else None
+        tag = name + (f"_c{ref.shape[-1]}_{ref.numel() // ref.shape[-1]}" if ref is not None and ref.dim() > 1 else "")
+    elif name == "rmsprop_step":
+        nbytes = 5 * _nbytes(a[0])
+    return dict(op=tag, flops=flops, bytes=nbytes, kind="conv" if flops else "bw")
+
+
+class _Recorder:
+    """Wraps hgb200.ops during a plan's first eager pass to label every launch closure (no effect afterwards)."""
+
+    def __init__(self, real):
+        self.real = real
+        self.calls: List[dict] = []
+
+    def __getattr__(self, name):
+        fn = getattr(self.real, name)
+        if not callable(fn):
+            return fn
+
+        def wrapped(*a, **k):
+            self.calls.append(_describe(name, a, k))
+            return fn(*a, **k)
+
+        return wrapped
+
+
 # ================================================================================================ plan
 class TrainPlan:
     def __init__(self, eng: "TrainEngine", n: int, h: int, w: int):
@@ -245,8 +306,7 @@ class TrainPlan:
         self.fwd: List[Callable] = []
         self.bwd: List[Callable] = []
         self.post: List[Callable] = []
-        self.meta_fwd: List[str] = []
-        self.meta_bwd: List[str] = []
+        self.meta: List[dict] = []          # one entry per closure of launches("step"), filled by the first eager pass
         self.nodes: List[dict] = []
         self.grad_scale = 1.0          # 1/world_size: the sum over ranks is the global-batch mean
         self.use_target_weight = True
@@ -280,6 +340,28 @@ class TrainPlan:
         else:
             for fn in self.launches(which):
                 fn()
+
+    def profile(self, iters: int = 1):
+        """Eager replay of the whole step with a CUDA-event pair around every closure (on the launching stream).
+        Returns per-closure milliseconds averaged over `iters`, aligned with self.meta."""
+        dev = self.eng.device
+        st = torch.cuda.current_stream(dev)
+        fns = self.launches("step")
+        total = [0.0] * len(fns)
+        for _ in range(iters):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(fns) + 1)]
+            evs[0].record(st)
+            for i, fn in enumerate(fns):
+                fn()
+                evs[i + 1].record(st)
+            torch.cuda.synchronize(dev)
+            for i in range(len(fns)):
+                total[i] += evs[i].elapsed_time(evs[i + 1])
+        return [t / iters for t in total]
+
+    @property
+    def num_kernel_launches(self) -> int:
+        return sum(m.get("launches", 1) for m in self.meta)
 
     def _capture(self, which: str):
         # PLAIN capture of the closures; the caller must have run the list eagerly once before (module loading,
@@ -633,9 +715,20 @@ class TrainEngine:
             keep = [(a.clone(), b.clone(), c.clone()) for a, b, c in bufs]
             s = torch.cuda.Stream(device=self.device)
             s.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(s):
-                for fn in p.launches("step"):
-                    fn()
+            global ops
+            rec = _Recorder(ops)
+            real_ops, ops = ops, rec
+            try:
+                with torch.cuda.stream(s):
+                    for fn in p.launches("step"):
+                        rec.calls = []
+                        fn()
+                        c = rec.calls
+                        p.meta.append(dict(op=c[0]["op"] if c else "memset", flops=sum(x["flops"] for x in c),
+                                           bytes=sum(x["bytes"] for x in c), kind=c[0]["kind"] if c else "bw",
+                                           launches=len(c)))
+            finally:
+                ops = real_ops
             torch.cuda.current_stream(self.device).wait_stream(s)
             torch.cuda.synchronize(self.device)
             ops.check_err_word(self.device)

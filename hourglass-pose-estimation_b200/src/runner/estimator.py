@@ -1,0 +1,93 @@
+"""Estimator with the reference's structure (src/runner/estimator.py:11-93).
+
+`post_process_heatmap_v2` keeps the reference's argument choice (center = frame centre, scale =
+frame*4/200/heat-map size): as SURVEY.md A14 records, that choice treats heat-map coordinates as if they were in
+frame space, so every keypoint lands within a few pixels of the frame centre -- the parity target is the
+FUNCTION get_final_preds_v1 with explicit arguments, and this caller is kept only so the entry point exists.
+`np.int` (removed in numpy 1.24, estimator.py:73,82) is spelled `int`.  cv2 is only needed by preprocess_bbox."""
+import os
+import time
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from src import models
+from src.utils.inference import get_final_preds_v1
+
+
+class Estimator:
+    def __init__(self, cfg, state_dict=None):
+        print(f"==> creating model '{cfg['MODEL']['arch']}', stacks={cfg['MODEL']['num_stacks']}")
+        self.model = models.__dict__[cfg['MODEL']['arch']](num_stacks=cfg['MODEL']['num_stacks'],
+                                                           num_blocks=1,
+                                                           num_classes=cfg['MODEL']['num_classes'],
+                                                           mobile=cfg['MODEL']['mobile'],
+                                                           skip_mode=cfg['MODEL']['skip_mode'],
+                                                           out_res=cfg['COMMON']['out_res'])
+        if not torch.cuda.is_available():
+            raise RuntimeError("Estimator (B200 build) needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device('cuda')
+        self.dataset = cfg['COMMON']['dataset']
+        self.input_size = (cfg['COMMON']['in_res'], cfg['COMMON']['in_res'])
+        self.threshold = 0.02
+        if state_dict is None:
+            if not os.path.isfile(cfg['COMMON']['resume']):
+                raise FileNotFoundError('Checkpoint not found')
+            checkpoint = torch.load(cfg['COMMON']['resume'], map_location=self.device)
+            state_dict = checkpoint['state_dict']
+        loaded_dict = OrderedDict()
+        for k, v in state_dict.items():
+            loaded_dict[k[7:] if k.startswith('module.') else k] = v
+        self.model.load_state_dict(loaded_dict)
+        self.model.to(self.device)
+        self.model.eval()
+
+    def preprocess_bbox(self, bbox):
+        import cv2
+        in_frame = bbox / 255.0
+        if 'coco' in self.dataset:
+            in_frame = (in_frame - np.array([[[0.4003, 0.4314, 0.4534]]])) / np.array([[[0.2466, 0.2467, 0.2562]]])
+        elif 'mpii' in self.dataset:
+            in_frame = (in_frame - np.array([[[0.4327, 0.4440, 0.4404]]])) / np.array([[[0.2468, 0.2410, 0.2458]]])
+        elif 'merl' in self.dataset:
+            in_frame = (in_frame - np.array([[[0.4785, 0.5036, 0.5078]]])) / np.array([[[0.2306, 0.2289, 0.2326]]])
+        elif 'se7en11' in self.dataset:
+            in_frame = (in_frame - np.array([[[0.5109, 0.5502, 0.5285]]])) / np.array([[[0.2772, 0.2416, 0.2478]]])
+        in_frame = cv2.resize(in_frame, self.input_size)
+        in_frame = in_frame.transpose((2, 0, 1))
+        in_frame = in_frame.reshape((1, 3, self.input_size[0], self.input_size[1]))
+        return torch.from_numpy(in_frame).float().to(self.device)
+
+    def post_process_heatmap_v1(self, heatmaps, output_size):
+        heatmaps = heatmaps.cpu().numpy()[0]
+        kplst = []
+        for i in range(heatmaps.shape[0]):
+            _map = heatmaps[i, :, :]
+            ind = np.unravel_index(np.argmax(_map), _map.shape)
+            if _map[ind] > self.threshold:
+                kplst.append((int(ind[1]), int(ind[0]), _map[ind]))
+            else:
+                kplst.append((0, 0, 0))
+        kplst = np.array(kplst)
+        scale_x = output_size[0] * 1.0 / self.input_size[0]
+        scale_y = output_size[1] * 1.0 / self.input_size[1]
+        kps = [kplst[:, 0] * scale_x * 4, kplst[:, 1] * scale_y * 4]
+        return np.asarray(kps, dtype=int).transpose()
+
+    @staticmethod
+    def post_process_heatmap_v2(heatmap, output_size):
+        center = np.array([round(output_size[0] * 0.5), round(output_size[1] * 0.5)])
+        scale = np.array([output_size[0] * 4.0 / 200 / heatmap.shape[2],
+                          output_size[1] * 4.0 / 200 / heatmap.shape[3]])
+        kps = get_final_preds_v1(heatmap, center, scale, output_size)
+        return kps.astype(int)
+
+    def run(self, frame):
+        in_frame = self.preprocess_bbox(frame)
+        start = time.time()
+        with torch.no_grad():
+            heatmaps = self.model(in_frame)[-1].detach()
+        end = time.time()
+        print(f"Inference time on {self.device}: %0.3f" % (end - start))
+        return self.post_process_heatmap_v2(heatmaps, (frame.shape[1], frame.shape[0]))

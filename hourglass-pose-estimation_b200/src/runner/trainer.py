@@ -1,0 +1,177 @@
+"""Trainer with the reference's structure (src/runner/trainer.py:15-181) on the sm_100a training engine.
+
+What changes against the reference: `torch.nn.DataParallel` (trainer.py:37: per-step parameter broadcast,
+GIL-bound replica threads, loss/optimizer on GPU 0) becomes ONE PROCESS PER GPU under torchrun -- each rank
+runs the fused step (hgb200.train.TrainEngine.train_step) on its batch shard, BatchNorm uses the shard's
+statistics exactly as DataParallel replicas do, the flat gradient buffer is summed by ONE NCCL all-reduce
+over NVLink (the local loss is pre-scaled by 1/world so the sum is the global-batch mean), and RMSprop is a
+single fused launch over the flat parameter buffer.  Datasets are out of scope: the
+loaders are passed in; anything yielding (images, heatmaps, {'target_weight': ...}) works.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from src.loss.mse import MSELoss
+from src import models
+from src.utils.evaluation import AverageMeter, accuracy
+from hgb200.train import train_engine, RMSPROP_ALPHA, RMSPROP_EPS
+
+
+def adjust_learning_rate(optimizer, epoch, lr, schedule, gamma):
+    """Sets the learning rate to the initial LR decayed by schedule (trainer.py:15-21)."""
+    if epoch in schedule:
+        lr *= gamma
+        for param_group in optimizer.param_groups:
+            param_group['lr'] = lr
+    return lr
+
+
+class FusedRMSprop(object):
+    """torch.optim.RMSprop(lr, momentum=0, weight_decay=0) (trainer.py:39-41) as one launch over the flat
+    parameter / gradient / square-average buffers.  Exposes what the reference touches: param_groups (for
+    adjust_learning_rate), zero_grad, step, state_dict / load_state_dict."""
+
+    def __init__(self, engine, lr):
+        self.engine = engine
+        self.param_groups = [{'lr': lr, 'alpha': RMSPROP_ALPHA, 'eps': RMSPROP_EPS, 'momentum': 0, 'weight_decay': 0}]
+
+    def zero_grad(self, set_to_none=False):
+        pass                            # the step's backward pass starts by zeroing the flat gradient buffer
+
+    def step(self):
+        g = self.param_groups[0]
+        self.engine.rmsprop(g['lr'], g['alpha'], g['eps'])
+
+    def state_dict(self):
+        st = self.engine.store
+        return {'param_groups': self.param_groups,
+                'square_avg': {k: st.view(st.V, k).detach().clone().contiguous() for k in st.slots}}
+
+    def load_state_dict(self, sd):
+        self.param_groups = sd['param_groups']
+        st = self.engine.store
+        for k, v in sd['square_avg'].items():
+            st.view(st.V, k).copy_(v)
+
+
+class Trainer(object):
+    def __init__(self, cfg, num_classes, train_loader=None, val_loader=None):
+        self.cfg = cfg
+        self.rank = int(os.environ.get('RANK', 0))
+        self.world = int(os.environ.get('WORLD_SIZE', 1))
+        local_rank = int(os.environ.get('LOCAL_RANK', 0))
+        if not torch.cuda.is_available():
+            raise RuntimeError("Trainer (B200 build) needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device('cuda', local_rank)
+        torch.cuda.set_device(self.device)
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group(backend='nccl', device_id=self.device)
+        if self.rank == 0:
+            print(f"==> creating model '{cfg['MODEL']['arch']}', stacks={cfg['MODEL']['num_stacks']}")
+        torch.manual_seed(cfg.get('COMMON', {}).get('seed', 0))      # identical initial weights on every rank
+        model = models.__dict__[cfg['MODEL']['arch']](num_stacks=cfg['MODEL']['num_stacks'],
+                                                      num_blocks=1,
+                                                      num_classes=num_classes,
+                                                      mobile=cfg['MODEL']['mobile'],
+                                                      skip_mode=cfg['MODEL']['skip_mode'],
+                                                      out_res=cfg['DATASET']['out_res'])
+        self.model = model.to(self.device)
+        self.engine = train_engine(self.model)
+        self.optimizer = FusedRMSprop(self.engine, cfg['TRAIN']['learning_rate'])
+        self.criterion = MSELoss(use_target_weight=True)
+        self.start_epoch = 0
+        self.best_acc = 0
+        self.train_loader = train_loader
+        self.val_loader = val_loader
+        self.idxs = cfg['MODEL']['subset']
+        if os.path.isfile(cfg['COMMON'].get('resume', '') or ''):
+            self._resume()
+
+    # ------------------------------------------------------------------ checkpoints (reference format)
+    def _resume(self):
+        checkpoint = torch.load(self.cfg['COMMON']['resume'], map_location=self.device)
+        self.start_epoch = checkpoint['epoch']
+        self.best_acc = checkpoint['best_acc']
+        sd = {(k[7:] if k.startswith('module.') else k): v for k, v in checkpoint['state_dict'].items()}
+        self.model.load_state_dict(sd)
+        if 'square_avg' in checkpoint.get('optimizer', {}):
+            self.optimizer.load_state_dict(checkpoint['optimizer'])
+
+    def state(self, epoch):
+        # keys carry the 'module.' prefix the reference's DataParallel wrapper adds (estimator.py:28-31 strips it)
+        return {'epoch': epoch + 1,
+                'state_dict': {'module.' + k: v.detach().clone().contiguous() for k, v in self.model.state_dict().items()},
+                'optimizer': self.optimizer.state_dict(),
+                'best_acc': self.best_acc}
+
+    # ------------------------------------------------------------------ one step / one epoch
+    def _all_reduce(self, flat_grads):
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+
+    def train_step(self, images, heatmaps, target_weight):
+        """trainer.py:82-99 for one batch shard.  Returns (loss device tensor [1], last heat maps)."""
+        lr = self.optimizer.param_groups[0]['lr']
+        loss = self.engine.train_step(images.to(self.device, non_blocking=True),
+                                      heatmaps.to(self.device, non_blocking=True),
+                                      target_weight.to(self.device, non_blocking=True), lr,
+                                      world_size=self.world,
+                                      all_reduce=self._all_reduce if self.world > 1 else None)
+        n, _, h, w = images.shape
+        return loss, self.engine.plans[(n, h, w)].outputs[-1]
+
+    def _train_epoch(self):
+        self.model.train()
+        average_loss = AverageMeter()
+        average_acc = AverageMeter()
+        for i, (images, heatmaps, meta) in enumerate(self.train_loader):
+            if self.idxs:
+                heatmaps = torch.index_select(heatmaps, 1, torch.LongTensor(self.idxs))
+            loss, last_hms = self.train_step(images, heatmaps, meta['target_weight'])
+            acc = accuracy(last_hms, heatmaps.to(self.device), self.idxs, thr=self.cfg['COMMON']['pck'])
+            average_loss.update(loss.item() * self.world, images.size(0))
+            average_acc.update(acc[0], images.size(0))
+        return average_loss.avg, average_acc.avg
+
+    def _evaluate(self):
+        self.model.eval()
+        average_loss = AverageMeter()
+        average_acc = AverageMeter()
+        with torch.no_grad():
+            for i, (images, heatmaps, meta) in enumerate(self.val_loader):
+                if self.idxs:
+                    heatmaps = torch.index_select(heatmaps, 1, torch.LongTensor(self.idxs))
+                images = images.to(self.device)
+                heatmaps = heatmaps.to(self.device, non_blocking=True)
+                target_weight = meta['target_weight'].to(self.device, non_blocking=True)
+                outputs = self.model(images)
+                last_hms = outputs[-1]
+                loss = self.criterion(outputs, heatmaps, target_weight)
+                acc = accuracy(last_hms, heatmaps, self.idxs, thr=self.cfg['COMMON']['pck'])
+                average_loss.update(loss.item(), images.size(0))
+                average_acc.update(acc[0], images.size(0))
+        is_best = False
+        if average_acc.avg > self.best_acc:
+            is_best = True
+            self.best_acc = average_acc.avg
+        return average_loss.avg, average_acc.avg, is_best
+
+    def train(self):
+        only_checkpoint_path = os.path.join(self.cfg['COMMON']['checkpoint_dir'], 'ckpts')
+        if self.rank == 0 and not os.path.isdir(only_checkpoint_path):
+            os.makedirs(only_checkpoint_path)
+        lr = self.cfg['TRAIN']['learning_rate']
+        for epoch in range(self.start_epoch, self.cfg['TRAIN']['epochs'] + 1):
+            lr = adjust_learning_rate(self.optimizer, epoch, lr, self.cfg['TRAIN']['schedule'],
+                                      self.cfg['TRAIN']['gamma'])
+            if self.rank == 0:
+                print('\nEpoch: %d | LR: %.8f' % (epoch + 1, lr))
+            loss, acc = self._train_epoch()
+            val_loss, val_acc, is_best = self._evaluate()
+            if self.rank == 0 and ((epoch + 1) % self.cfg['COMMON']['snapshot'] == 0 or is_best):
+                state = self.state(epoch)
+                if (epoch + 1) % self.cfg['COMMON']['snapshot'] == 0:
+                    torch.save(state, os.path.join(only_checkpoint_path, f'checkpoint_{epoch+1}.pth.tar'))
+                if is_best:
+                    torch.save(state, os.path.join(only_checkpoint_path, 'best.pth.tar'))

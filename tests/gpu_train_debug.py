@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path[:0] = [os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), "hourglass-pose-estimation_b200")]
+sys.path[:0] = [os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), "hourglass-pose-estimation_b200"), HERE]
 from hgb200 import ops  # noqa: E402
 
 torch.backends.cudnn.allow_tf32 = False
@@ -131,12 +131,42 @@ def t_pack_rms():
     return f"pack fwd {e0:.1e} dgrad {e1:.1e} rmsprop {e2:.1e} small_gemm {e3:.1e} {'OK' if ok else 'FAIL'}"
 
 
-def t_step(S, J, B, H, W, steps=2, lr=2.5e-4, use_graph=True, autograd=False):
+def load_emulation():
+    """A second instance of hgb200.train whose `ops` is the CPU torch emulation (tests/fake_ops.py)."""
+    import importlib.util
+    import fake_ops
+    path = os.path.join(os.path.dirname(HERE), "hourglass-pose-estimation_b200", "hgb200", "train.py")
+    spec = importlib.util.spec_from_file_location("hgb200.train_emulation", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.ops = fake_ops
+    mod._TEST_ALLOW_CPU = True
+    return mod
+
+
+def grad_rows(grads, ref_grads):
+    rows = []
+    for k, gref in ref_grads.items():
+        gm, gr = grads[k].reshape(-1).double(), gref.reshape(-1).double()
+        nr = float(gr.norm())
+        rows.append((float((gm * gr).sum() / (gm.norm() * gr.norm() + 1e-300)), float((gm - gr).norm() / (nr + 1e-300)), nr, k))
+    return rows
+
+
+def summarize(tag, rows):
+    gmax = max(w[2] for w in rows)
+    sig = sorted(w for w in rows if w[2] > 1e-4 * gmax)
+    return (f"{tag}: {len(sig)} significant grads, min cos {sig[0][0]:.4f}, median relL2 "
+            f"{np.median([w[1] for w in sig]):.3e}, max relL2 {max(w[1] for w in sig):.3e}"), sig
+
+
+def t_step(S, J, B, H, W, steps=2, lr=2.5e-4, use_graph=True, autograd=False, emulate=True):
     from src.models import hg
     from src.loss import MSELoss
     from oracle.hourglass_oracle import make_state_dict
     from oracle import train_oracle as T
     from oracle.make_golden_inputs import train_inputs
+    from test_train_plan_cpu import autocast_yardstick
     torch.set_num_threads(min(16, os.cpu_count() or 1))
     sd = make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, seed=0)
     model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum")
@@ -145,6 +175,13 @@ def t_step(S, J, B, H, W, steps=2, lr=2.5e-4, use_graph=True, autograd=False):
     batches = train_inputs(1, B, J, H, W, steps)
     from hgb200.train import train_engine
     eng = train_engine(model)
+    emu = emu_model = None
+    if emulate:
+        em = load_emulation()
+        emu_model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum")
+        emu_model.load_state_dict(sd)
+        emu_model.train()
+        emu = em.TrainEngine(emu_model, "cpu")
     sd_ref = {k: v.clone() for k, v in sd.items()}
     state = {}
     lines = []
@@ -152,6 +189,7 @@ def t_step(S, J, B, H, W, steps=2, lr=2.5e-4, use_graph=True, autograd=False):
     crit = MSELoss(use_target_weight=True)
     for step, (x, tg, tw) in enumerate(batches):
         t0 = time.time()
+        ac_loss, ac_outs, ac_grads = autocast_yardstick(sd_ref, x, tg, tw)
         ref_loss, ref_outs, ref_grads = T.forward_backward(sd_ref, x, tg, tw)
         t_ref = time.time() - t0
         if autograd:
@@ -170,23 +208,28 @@ def t_step(S, J, B, H, W, steps=2, lr=2.5e-4, use_graph=True, autograd=False):
             ops.check_err_word()
             loss = float(plan.loss)
             outs = plan.outputs
+        mine = {k: model.state_dict(keep_vars=True)[k].grad.detach().cpu().contiguous() for k in ref_grads}
         hm_err = max(rel(o.cpu(), r) for o, r in zip(outs, ref_outs))
-        worst = []
-        for k, gref in ref_grads.items():
-            gmine = model.state_dict(keep_vars=True)[k].grad
-            gm = gmine.detach().cpu().contiguous().reshape(-1).double()
-            gr = gref.reshape(-1).double()
-            nr = float(gr.norm())
-            cos = float((gm * gr).sum() / (gm.norm() * gr.norm() + 1e-300))
-            l2 = float((gm - gr).norm() / (nr + 1e-300))
-            worst.append((cos, l2, nr, k))
-        gmax = max(w[2] for w in worst)
-        sig = [w for w in worst if w[2] > 1e-5 * gmax]
-        sig.sort()
-        lines.append(f"  step {step}: loss {loss:.6e} ref {ref_loss:.6e} (rel {abs(loss - ref_loss) / ref_loss:.2e}) heatmap err {hm_err:.3e}; "
-                     f"{len(sig)} significant grads: min cos {sig[0][0]:.4f} max relL2 {max(w[1] for w in sig):.3e} (oracle {t_ref:.1f}s)")
-        for cos, l2, nr, k in sig[:6]:
-            lines.append(f"      {k}: cos {cos:.4f} relL2 {l2:.3e} |g| {nr:.3e}")
+        hm_ac = max(rel(o.float(), r) for o, r in zip(ac_outs, ref_outs))
+        lines.append(f"  step {step}: loss {loss:.6e} ref {ref_loss:.6e} (rel {abs(loss - ref_loss) / ref_loss:.2e}; autocast "
+                     f"{abs(ac_loss - ref_loss) / ref_loss:.2e}) heatmap err vs fp32 {hm_err:.3e} (autocast {hm_ac:.3e}) oracle {t_ref:.1f}s")
+        msg, sig = summarize("      vs fp32 oracle", grad_rows(mine, ref_grads))
+        lines.append(msg)
+        lines.append(summarize("      stock autocast vs fp32", grad_rows(ac_grads, ref_grads))[0])
+        if emu is not None:
+            t0 = time.time()
+            eplan = emu.plan_for(B, H, W)
+            eplan.input.copy_(x)
+            eplan.target.copy_(tg)
+            eplan.target_weight.copy_(tw.reshape(B, J))
+            eplan.run("step", False)
+            egr = {k: emu_model.state_dict(keep_vars=True)[k].grad.detach().contiguous().clone() for k in ref_grads}
+            hm_e = max(rel(o.cpu(), r) for o, r in zip(outs, eplan.outputs))
+            msg, sige = summarize(f"      vs bf16 emulation (loss rel {abs(loss - float(eplan.loss)) / float(eplan.loss):.2e}, "
+                                  f"heatmap {hm_e:.3e}, {time.time() - t0:.1f}s)", grad_rows(mine, egr))
+            lines.append(msg)
+            for cos, l2, nr, k in sige[:5]:
+                lines.append(f"          {k}: cos {cos:.4f} relL2 {l2:.3e} |g| {nr:.3e}")
         # optimizer
         T.rmsprop_update(sd_ref, ref_grads, state, lr)
         if autograd:
@@ -194,9 +237,15 @@ def t_step(S, J, B, H, W, steps=2, lr=2.5e-4, use_graph=True, autograd=False):
         else:
             eng.rmsprop(lr)
         torch.cuda.synchronize()
-        dp = max(float((model.state_dict()[k].detach().cpu() - sd_ref[k]).abs().max()) for k in ref_grads)
+        d = torch.cat([(model.state_dict()[k].detach().cpu() - sd_ref[k]).abs().reshape(-1) for k in ref_grads])
         bn_err = max(rel(model.state_dict()[k].cpu().float(), sd_ref[k].float()) for k in sd_ref if k.endswith("running_var"))
-        lines.append(f"      after update: max |dparam| {dp:.3e} (one step moves <= {lr / np.sqrt(1 - 0.99):.2e}); running_var rel err {bn_err:.2e}")
+        lines.append(f"      after update: |dparam| max {float(d.max()):.3e} median {float(d.median()):.3e} (one step moves "
+                     f"{lr / np.sqrt(1 - 0.99):.2e}); running_var rel err {bn_err:.2e}")
+        model.load_state_dict(sd_ref)          # continue from the oracle's parameters
+        if emu is not None:
+            emu_model.load_state_dict(sd_ref)
+        if autograd:
+            opt = torch.optim.RMSprop(model.parameters(), lr=lr)
     return "\n" + "\n".join(lines)
 
 
