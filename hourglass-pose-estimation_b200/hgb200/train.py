@@ -751,7 +751,8 @@ class TrainEngine:
     def train_step(self, x: torch.Tensor, target: torch.Tensor, target_weight: Optional[torch.Tensor], lr: float, *,
                    use_graph: bool = True, world_size: int = 1, all_reduce: Optional[Callable] = None) -> torch.Tensor:
         """One fused step: forward, JointsMSE loss, backward, (all-reduce,) RMSprop.  Returns the plan's loss
-        tensor (device, fp32 [1]; the LOCAL loss already scaled by 1/world_size)."""
+        tensor (device, fp32 [1]): the mean loss of THIS rank's shard; only the gradients carry the 1/world_size
+        factor, so that their sum over ranks is the gradient of the global-batch mean."""
         n, _, h, w = x.shape
         plan = self.plan_for(n, h, w)
         plan.input.copy_(x, non_blocking=True)

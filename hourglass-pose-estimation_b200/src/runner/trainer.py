@@ -130,7 +130,7 @@ class Trainer(object):
                 heatmaps = torch.index_select(heatmaps, 1, torch.LongTensor(self.idxs))
             loss, last_hms = self.train_step(images, heatmaps, meta['target_weight'])
             acc = accuracy(last_hms, heatmaps.to(self.device), self.idxs, thr=self.cfg['COMMON']['pck'])
-            average_loss.update(loss.item() * self.world, images.size(0))
+            average_loss.update(loss.item(), images.size(0))
             average_acc.update(acc[0], images.size(0))
         return average_loss.avg, average_acc.avg
 

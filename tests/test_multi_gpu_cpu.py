@@ -1,0 +1,96 @@
+"""N>1 host logic on CPU with world_size=2 over gloo: batch sharding, and the data-parallel training step
+(local loss scaled by 1/world, one all-reduce of the flat gradient buffer, identical RMSprop update on every
+rank) against the fp32 training oracle run per shard.  The kernels are emulated (tests/fake_ops.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+for p in (REPO, os.path.join(REPO, "hourglass-pose-estimation_b200"), HERE):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def test_batch_shard_partitions_the_batch():
+    from hgb200.shard import batch_shard
+    for total in (0, 1, 5, 8, 128, 1024, 1023):
+        for world in (1, 2, 4, 8):
+            spans = [batch_shard(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and b >= a
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert [batch_shard(3, 8, r) for r in range(8)][3:] == [(3, 3)] * 5        # B < N: high ranks idle
+    with pytest.raises(ValueError):
+        batch_shard(4, 2, 2)
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        import fake_ops
+        import hgb200.train as tr
+        from hgb200.shard import batch_shard, all_reduce_sum
+        from oracle.hourglass_oracle import make_state_dict
+        from oracle import train_oracle as T
+        from oracle.make_golden_inputs import train_inputs
+        from src.models import hg
+        tr.ops, tr._TEST_ALLOW_CPU, tr._ACT = fake_ops, True, torch.float32
+        fake_ops.BF = torch.float32
+        S, J, B, H, W, lr = 1, 16, 8, 128, 128, 2.5e-4
+        sd = make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, seed=0)
+        model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum")
+        model.load_state_dict(sd)
+        model.train()
+        eng = tr.TrainEngine(model, "cpu")
+        x, tg, tw = train_inputs(1, B, J, H, W, 1)[0]
+        a, b = batch_shard(B, world, rank)
+        loss = eng.train_step(x[a:b], tg[a:b], tw[a:b], lr, use_graph=False, world_size=world, all_reduce=all_reduce_sum)
+        # oracle: every shard separately (per-replica BN statistics), loss scaled by 1/world, gradients summed
+        total, ref_loss = None, 0.0
+        for r in range(world):
+            ra, rb = batch_shard(B, world, r)
+            l, _, g = T.forward_backward({k: v.clone() for k, v in sd.items()}, x[ra:rb], tg[ra:rb], tw[ra:rb],
+                                         grad_scale=1.0 / world)
+            ref_loss += l / world
+            total = g if total is None else {k: total[k] + g[k] for k in g}
+        worst = 0.0
+        sdk = model.state_dict(keep_vars=True)
+        gmax = max(float(v.norm()) for v in total.values())
+        for k, gr in total.items():
+            if float(gr.norm()) > 1e-4 * gmax:
+                gm = sdk[k].grad.detach().contiguous()
+                worst = max(worst, float((gm - gr).norm() / gr.norm()))
+        # global-batch loss = mean of the shard losses (the returned loss is the shard's own mean)
+        lt = loss.detach().clone()
+        dist.all_reduce(lt)
+        lt /= world
+        # parameters must be bit-identical on all ranks after the update
+        flat = eng.store.P.clone()
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        same = all(torch.equal(gathered[0], t) for t in gathered)
+        if rank == 0:
+            ret["worst"], ret["loss"], ret["ref_loss"], ret["same"] = worst, float(lt), ref_loss, same
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_step_world2_gloo():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret["same"], "ranks diverged after the all-reduced update"
+    assert abs(ret["loss"] - ret["ref_loss"]) <= 1e-4 * ret["ref_loss"]
+    assert ret["worst"] < 5e-2, ret["worst"]
