@@ -440,24 +440,31 @@ __global__ void __launch_bounds__(kThreads) rmsprop_kernel(float4* p, const floa
 }
 
 // ---------------------------------------------------------------- tiny strided fp32 GEMM (parameter space only)
-// C[i][j] = beta*C[i][j] + (D ? D[i][j] : 0) + sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj]
+// C[i][j] = beta*C[i][j] + (D ? D[i][j] : 0) + sum_k A[i*sai + k*sak] * B[k*sbk + j*sbj];  one warp per output,
+// the k range split over the lanes and combined by shuffles.
 __global__ void __launch_bounds__(kThreads) small_gemm_kernel(float* C, const float* __restrict__ A, const float* __restrict__ B,
                                                                const float* __restrict__ D, int m, int n, int k, int sai,
                                                                int sak, int sbk, int sbj, int sci, int scj, float beta) {
     pdl_launch_dependents();
     pdl_wait();
     const long long total = static_cast<long long>(m) * n;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = static_cast<long long>(gridDim.x) * (kThreads / 32);
+    for (long long idx = static_cast<long long>(blockIdx.x) * (kThreads / 32) + (threadIdx.x >> 5); idx < total; idx += warps) {
         const int i = static_cast<int>(idx / n), j = static_cast<int>(idx - static_cast<long long>(i) * n);
         float s = 0.f;
-        for (int kk = 0; kk < k; ++kk) s = fmaf(A[static_cast<long long>(i) * sai + static_cast<long long>(kk) * sak],
-                                                 B[static_cast<long long>(kk) * sbk + static_cast<long long>(j) * sbj], s);
-        float* c = C + static_cast<long long>(i) * sci + static_cast<long long>(j) * scj;
-        float r = s;
-        if (beta != 0.f) r += beta * *c;
-        if (D != nullptr) r += D[static_cast<long long>(i) * sci + static_cast<long long>(j) * scj];
-        *c = r;
+        for (int kk = lane; kk < k; kk += 32)
+            s = fmaf(A[static_cast<long long>(i) * sai + static_cast<long long>(kk) * sak],
+                     B[static_cast<long long>(kk) * sbk + static_cast<long long>(j) * sbj], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            float* c = C + static_cast<long long>(i) * sci + static_cast<long long>(j) * scj;
+            float r = s;
+            if (beta != 0.f) r += beta * *c;
+            if (D != nullptr) r += D[static_cast<long long>(i) * sci + static_cast<long long>(j) * scj];
+            *c = r;
+        }
     }
 }
 
@@ -636,8 +643,8 @@ extern "C" int hg_small_gemm_f32(float* c, const float* a, const float* b, const
         set_last_error("hg_small_gemm_f32: bad arguments");
         return HG_ERR_INVALID;
     }
-    const long long items = static_cast<long long>(m) * n;
-    HG_CUDA_OK(launch_kernel(small_gemm_kernel, dim3(grid_for((items + kThreads - 1) / kThreads)), dim3(kThreads), 0,
+    const long long items = static_cast<long long>(m) * n;      // one warp per output
+    HG_CUDA_OK(launch_kernel(small_gemm_kernel, dim3(grid_for((items + kThreads / 32 - 1) / (kThreads / 32))), dim3(kThreads), 0,
                              static_cast<cudaStream_t>(stream), c, a, b, d, m, n, k, sai, sak, sbk, sbj, sci, scj, beta));
     return HG_OK;
 }
