@@ -294,6 +294,14 @@ def run_train(args):
         c["ms"] += ms
         c["n"] += 1
     total_ms = sum(per)
+    # launch DAG (hgb200/dag.py): the longest dependency chain, priced with the per-launch eager times
+    import hgb200.train as _tr
+    d, stream_of, waits = plan.schedule("step")
+    fin = [0.0] * d.n
+    for i in range(d.n):
+        fin[i] = per[i] + max((fin[q] for q in d.preds[i]), default=0.0)
+    dag_info = {"streams": _tr.STREAMS, "launch_closures": d.n, "edges": sum(len(q) for q in d.preds),
+                "cross_stream_edges": sum(len(q) for q in waits), "sum_of_launch_ms": total_ms, "critical_path_ms": max(fin)}
     top_name, top = max(classes.items(), key=lambda kv: kv[1]["ms"])
     avg_ms = top["ms"] / top["n"]
     if top["kind"] == "conv" and top["flops"] / max(top["bytes"], 1) > tf_sustained * 1e12 / (hbm_peak * 1e9):
@@ -307,6 +315,7 @@ def run_train(args):
         with open(args.breakdown, "w") as f:
             f.write(f"# train step, per-kernel-class device time, eager replay with CUDA events, batch {B}; total {total_ms:.3f} ms; "
                     f"graph step {ms_step:.3f} ms\n")
+            f.write(f"# launch DAG: {json.dumps(dag_info)}\n")
             f.write("class,launches,total_ms,avg_ms,share,TFLOP/s,GB/s\n")
             for name, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
                 a = c["ms"] / c["n"]
@@ -332,7 +341,7 @@ def run_train(args):
                    "weights": "random init (torch default)", "loss_first_last": [loss0, loss1]},
         "tensor_tflops": flops_per_step / (ms_step * 1e-3) / 1e12,
         "tensor_frac_of_measured_peak": flops_per_step / (ms_step * 1e-3) / 1e12 / tf_sustained,
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "launch_dag": dag_info,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * H * W * 4 + 2 * B * J * 3 * 8,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": (plan.num_kernel_launches + 3) * steps,

@@ -391,7 +391,9 @@ __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_pad_kernel(const float*
 // ---------------------------------------------------------------- weight packing (table-driven, one launch)
 constexpr int kPackBlocksPerEntry = 8;
 __global__ void __launch_bounds__(kThreads) pack_weights_kernel(const hg_pack_entry* __restrict__ table, int n_entries) {
-    pdl_launch_dependents();
+    // NO early pdl_launch_dependents() here: the GEMM kernels fetch their weights BEFORE griddepcontrol.wait
+    // (constants on the inference path), and a chain of small grids can run that preamble several launches ahead.
+    // Without the early trigger nothing launched after this kernel starts until every packed weight is visible.
     pdl_wait();
     const int ei = blockIdx.x / kPackBlocksPerEntry;
     if (ei >= n_entries) return;

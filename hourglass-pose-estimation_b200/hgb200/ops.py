@@ -423,6 +423,11 @@ def sumpool2x2(dy: torch.Tensor, dlow: torch.Tensor, accumulate: bool = False):
     return dlow
 
 
+def zero_(t: torch.Tensor):
+    """Memset on the current stream (a named call so that launch recorders / the launch DAG see it)."""
+    return t.zero_()
+
+
 def add_inplace(dst: torch.Tensor, src: torch.Tensor):
     _require_cuda(dst, src)
     lib.check(lib.hg_add_inplace_bf16(_ptr(dst), _ptr(src), dst.numel(), _stream()), "hg_add_inplace_bf16")

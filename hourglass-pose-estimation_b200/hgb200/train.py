@@ -18,13 +18,14 @@ src/runner/trainer.py:82-99) as a static plan of sm_100a kernel launches.
 """
 from __future__ import annotations
 
+import os
 from collections import defaultdict
 from typing import Callable, Dict, List, Optional, Sequence
 
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import dag, ops
 from ._lib import HgError
 
 RMSPROP_ALPHA = 0.99      # torch.optim.RMSprop defaults (trainer.py:39-41 passes lr, momentum=0, weight_decay=0)
@@ -36,6 +37,9 @@ BN_MOMENTUM = 0.1
 # without a GPU; the product path never does (a CPU model raises below).
 _TEST_ALLOW_CPU = False
 _ACT = torch.bfloat16     # activation / GEMM-weight storage type (the same test switches it to fp32 for exact checks)
+# The step's launches are captured as a dependency DAG across this many CUDA streams (hgb200/dag.py);
+# 1 = one chain on one stream.
+STREAMS = int(os.environ.get("HG_TRAIN_STREAMS", "6"))
 
 
 def _pad(v: int, m: int) -> int:
@@ -98,16 +102,21 @@ class _T:
 
 
 class _Arena:
-    def __init__(self, device):
+    """Gradient buffers of the backward pass, recycled in emission order.  With the launch DAG a recycled buffer
+    is an edge (write-after-read) between otherwise independent launches, so reuse is first-in-first-out and only
+    once `depth` buffers of that shape are free: the edge then points several bottlenecks back."""
+
+    def __init__(self, device, depth: int = 1):
         self.device = device
         self.free = defaultdict(list)
         self.total_bytes = 0
+        self.depth = depth
 
     def get(self, shape, dtype=None):
         dtype = dtype or _ACT
         key = (tuple(shape), dtype)
-        if self.free[key]:
-            return self.free[key].pop()
+        if len(self.free[key]) >= self.depth:
+            return self.free[key].pop(0)
         t = torch.empty(shape, dtype=dtype, device=self.device)
         self.total_bytes += t.numel() * t.element_size()
         return t
@@ -117,8 +126,8 @@ class _Arena:
 
     def get_halo(self, n, h, w, c):
         key = ("halo", n, h, w, c)
-        if self.free[key]:
-            return self.free[key].pop()
+        if len(self.free[key]) >= self.depth:
+            return self.free[key].pop(0)
         t = ops.halo_padded_buffer(n, h, w, c, self.device)
         self.total_bytes += t.numel() * 2
         return t
@@ -282,7 +291,9 @@ class _Recorder:
             return fn
 
         def wrapped(*a, **k):
-            self.calls.append(_describe(name, a, k))
+            d = _describe(name, a, k)
+            d["acc"] = dag.accesses(name, a, k)
+            self.calls.append(d)
             return fn(*a, **k)
 
         return wrapped
@@ -307,6 +318,8 @@ class TrainPlan:
         self.bwd: List[Callable] = []
         self.post: List[Callable] = []
         self.meta: List[dict] = []          # one entry per closure of launches("step"), filled by the first eager pass
+        self.records: List[list] = []       # same alignment: tensor regions each closure reads / writes (hgb200/dag.py)
+        self.schedules: Dict[str, tuple] = {}
         self.nodes: List[dict] = []
         self.grad_scale = 1.0          # 1/world_size: the sum over ranks is the global-batch mean
         self.use_target_weight = True
@@ -317,7 +330,7 @@ class TrainPlan:
     # ---- launch lists
     def _loss_launches(self):
         def run():
-            self.loss.zero_()
+            ops.zero_(self.loss)
             ops.jmse_loss_into(self.outputs, self.dheat, self.target, self.target_weight if self.use_target_weight else None,
                                self.loss, grad_scale=self.grad_scale)
         return [run]
@@ -363,13 +376,37 @@ class TrainPlan:
     def num_kernel_launches(self) -> int:
         return sum(m.get("launches", 1) for m in self.meta)
 
+    def _slice(self, which: str):
+        """Index range of launches(which) inside launches("step") (meta / records are aligned with the latter)."""
+        n_pre_fwd = len(self.pre) + len(self.fwd)
+        n_loss = len(self._loss_launches())
+        total = n_pre_fwd + n_loss + len(self.bwd) + len(self.post)
+        return {"fwd": (0, n_pre_fwd), "bwd": (n_pre_fwd + n_loss, total), "step": (0, total)}[which]
+
+    def schedule(self, which: str, streams: Optional[int] = None):
+        """-> (dag, stream of each launch, cross-stream waits of each launch) for launches(which)."""
+        k = streams or STREAMS
+        sched = self.schedules.get((which, k))
+        if sched is None:
+            lo, hi = self._slice(which)
+            d = dag.build(self.records[lo:hi])
+            cost = [4e-6 + max(m["flops"] / 6e14, m["bytes"] / 3e12) for m in self.meta[lo:hi]]
+            stream_of, waits = dag.assign_streams(d, cost, k)
+            sched = self.schedules[(which, k)] = (d, stream_of, waits)
+        return sched
+
     def _capture(self, which: str):
-        # PLAIN capture of the closures; the caller must have run the list eagerly once before (module loading,
-        # shared-memory opt-in) -- TrainEngine.plan_for() does that on a scratch copy of the BN statistics.
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for fn in self.launches(which):
-                fn()
+        # The caller must have run the list eagerly once before (module loading, shared-memory opt-in, access
+        # records) -- TrainEngine.plan_for() does that on a scratch copy of the BN statistics.
+        fns = self.launches(which)
+        if STREAMS > 1:
+            _, stream_of, waits = self.schedule(which)
+            g = dag.capture(fns, stream_of, waits, STREAMS, self.eng.device)
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for fn in fns:
+                    fn()
         self.graphs[which] = g
         return g
 
@@ -557,7 +594,7 @@ class TrainEngine:
         plan.fwd_bytes = fwd_bytes[0]
 
         # ---- pre: zero the per-step scratch, merge the remap weights, pack every GEMM weight (one launch)
-        plan.pre.append(lambda: self.stat.zero_())
+        plan.pre.append(lambda: ops.zero_(self.stat))
         for rm in self.remap:
             plan.pre.append(lambda rm=rm: rm.merge(self.ones))
         plan.pre.append(lambda: ops.pack_weights(self.pack_table, len(self.pack_entries)))
@@ -571,9 +608,9 @@ class TrainEngine:
     def _emit_backward(self, plan: TrainPlan):
         dev = self.device
         B = plan.bwd
-        arena = _Arena(dev)
+        arena = _Arena(dev, depth=3 if STREAMS > 1 else 1)
         G = self.store.G
-        B.append(lambda: G.zero_())
+        B.append(lambda: ops.zero_(G))
 
         def release(t: _T):
             if t.grad is not None and t.grad_owned:
@@ -706,32 +743,39 @@ class TrainEngine:
         p = self.plans.get(key)
         if p is None:
             p = self.build_plan(n, h, w)
-            if self.device.type != "cuda":          # host-logic tests only (_TEST_ALLOW_CPU)
-                self.plans[key] = p
-                return p
-            # one eager pass on a side stream with the BN running statistics preserved: loads every kernel and opts
-            # in to large shared memory before any graph capture
+            # one eager pass with the BN running statistics preserved: loads every kernel and opts in to large
+            # shared memory before any graph capture, and records what every launch reads and writes (launch DAG,
+            # roofline accounting).  On a side stream when on the GPU.
+            cuda = self.device.type == "cuda"          # else: host-logic tests only (_TEST_ALLOW_CPU)
             bufs = [(b.rm, b.rv, b.nbt) for b in self._bns]
             keep = [(a.clone(), b.clone(), c.clone()) for a, b, c in bufs]
-            s = torch.cuda.Stream(device=self.device)
-            s.wait_stream(torch.cuda.current_stream(self.device))
             global ops
             rec = _Recorder(ops)
             real_ops, ops = ops, rec
+
+            def record():
+                for fn in p.launches("step"):
+                    rec.calls = []
+                    fn()
+                    c = rec.calls
+                    p.meta.append(dict(op=c[0]["op"] if c else "memset", flops=sum(x["flops"] for x in c),
+                                       bytes=sum(x["bytes"] for x in c), kind=c[0]["kind"] if c else "bw",
+                                       launches=len(c)))
+                    p.records.append([x["acc"] for x in c])
             try:
-                with torch.cuda.stream(s):
-                    for fn in p.launches("step"):
-                        rec.calls = []
-                        fn()
-                        c = rec.calls
-                        p.meta.append(dict(op=c[0]["op"] if c else "memset", flops=sum(x["flops"] for x in c),
-                                           bytes=sum(x["bytes"] for x in c), kind=c[0]["kind"] if c else "bw",
-                                           launches=len(c)))
+                if cuda:
+                    s = torch.cuda.Stream(device=self.device)
+                    s.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(s):
+                        record()
+                    torch.cuda.current_stream(self.device).wait_stream(s)
+                    torch.cuda.synchronize(self.device)
+                else:
+                    record()
             finally:
                 ops = real_ops
-            torch.cuda.current_stream(self.device).wait_stream(s)
-            torch.cuda.synchronize(self.device)
-            ops.check_err_word(self.device)
+            if cuda:
+                ops.check_err_word(self.device)
             for (a, b, c), (ka, kb, kc) in zip(bufs, keep):
                 a.copy_(ka)
                 b.copy_(kb)

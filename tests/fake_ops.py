@@ -85,6 +85,10 @@ def sumpool2x2(dy, dlow, accumulate=False):
     return _store(dlow, g)
 
 
+def zero_(t):
+    return t.zero_()
+
+
 def add_inplace(dst, src):
     dst.copy_((dst.float() + src.float()).to(dst.dtype))
     return dst

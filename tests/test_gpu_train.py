@@ -256,6 +256,32 @@ def test_step_noise_is_stock_bf16_level():
             assert float((model.state_dict()[k].cpu() - sd_ref[k]).abs().max()) < 0.05
 
 
+def test_multi_stream_graph_agrees_with_one_stream(monkeypatch):
+    """The step captured as a launch DAG over several streams (hgb200/dag.py) against the one-stream chain: same
+    loss to the run-to-run noise of the fp32 atomics (two identical one-stream runs differ by ~0.4 %), no device
+    error word, every buffer finite.  (The dependency analysis itself is proven on CPU by executing random
+    topological orders: tests/test_train_dag_cpu.py.)"""
+    import hgb200.train as tr
+    S, J, B, H, W = 2, 16, 4, 128, 128
+    x, tg, tw = train_inputs(1, B, J, H, W, 1)[0]
+    losses = {}
+    for k in (1, 6):
+        monkeypatch.setattr(tr, "STREAMS", k)
+        sd, model = _model(S, J)
+        eng = tr.TrainEngine(model)
+        losses[k] = [float(eng.train_step(x.cuda(), tg.cuda(), tw.cuda(), 2.5e-4)) for _ in range(2)]
+        torch.cuda.synchronize()
+        tr.ops.check_err_word()
+        plan = eng.plans[(B, H, W)]
+        assert torch.isfinite(eng.store.G).all() and torch.isfinite(eng.store.P).all()
+        assert all(torch.isfinite(o).all() for o in plan.outputs)
+        if k > 1:
+            _, stream_of, waits = plan.schedule("step")
+            assert len(set(stream_of)) > 1 and sum(len(w) for w in waits) > 100
+    assert abs(losses[6][0] - losses[1][0]) <= 2e-2 * losses[1][0]
+    assert abs(losses[6][1] - losses[1][1]) <= 8e-2 * losses[1][1]
+
+
 def test_loss_trajectory_tracks_the_oracle_and_decreases():
     from hgb200.train import train_engine
     S, J, B, H, W, steps, lr = 2, 16, 4, 128, 128, 6, 2.5e-4
@@ -267,8 +293,12 @@ def test_loss_trajectory_tracks_the_oracle_and_decreases():
     mine = []
     for x, tg, tw in batches:
         mine.append(float(eng.train_step(x.cuda(), tg.cuda(), tw.cuda(), lr)))
-    assert mine[-1] < 0.8 * mine[0]
-    np.testing.assert_allclose(mine, ref_losses, rtol=0.08)
+    assert mine[-1] < 0.5 * mine[0]
+    # first step: same weights, only bf16 noise.  Later steps: RMSprop's early updates have magnitude lr/sqrt(1-alpha)
+    # whatever the gradient's size, so the chaotic gradient noise (see module docstring) moves the trajectory: two
+    # runs of the SAME GPU path differ by up to +-20 % at step 6 (profiles/r1_train_dag_check.log)
+    assert abs(mine[0] - ref_losses[0]) <= 3e-2 * ref_losses[0]
+    np.testing.assert_allclose(mine, ref_losses, rtol=0.35)
     assert int(model.bn1.num_batches_tracked) == steps
 
 

@@ -1,0 +1,138 @@
+"""Launch DAG of the training step (hgb200/dag.py) on CPU: dependency analysis from byte ranges, stream
+assignment, and -- the real check -- the whole step executed in RANDOM topological orders of the DAG through
+the CPU emulation must give bit-identical gradients, heat maps, loss and BN statistics to the sequential order
+(any missing read-after-write / write-after-read edge, e.g. through a recycled gradient buffer, shows up)."""
+import os
+import random
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import fake_ops  # noqa: E402
+from hgb200 import dag  # noqa: E402
+from oracle.hourglass_oracle import make_state_dict  # noqa: E402
+from oracle.make_golden_inputs import train_inputs  # noqa: E402
+
+
+def _acc(reads=(), writes=()):
+    return [([("s", lo, hi) for lo, hi in reads], [("s", lo, hi) for lo, hi in writes])]
+
+
+def test_edges_from_byte_ranges():
+    recs = [
+        _acc(writes=[(0, 100)]),                 # 0 writes A
+        _acc(reads=[(0, 50)]),                   # 1 reads half of A            -> RAW on 0
+        _acc(reads=[(50, 100)]),                 # 2 reads the other half       -> RAW on 0
+        _acc(writes=[(0, 50)]),                  # 3 overwrites the first half  -> WAR on 1 (WAW on 0 is implied)
+        _acc(reads=[(0, 100)]),                  # 4 reads all                  -> RAW on 3 (0 implied)
+        _acc(writes=[(200, 300)]),               # 5 unrelated
+        [],                                      # 6 barrier
+        _acc(reads=[(200, 300)]),                # 7 after the barrier
+    ]
+    d = dag.build(recs)
+    assert d.preds[0] == [] and d.preds[1] == [0] and d.preds[2] == [0]
+    assert d.preds[3] == [1]
+    assert sorted(d.preds[4]) == [3]
+    assert d.preds[5] == []
+    assert sorted(d.preds[6]) == [2, 4, 5]
+    assert d.preds[7] == [6]
+    assert d.check_order(range(8)) and not d.check_order([1, 0, 2, 3, 4, 5, 6, 7])
+
+
+def test_stream_assignment_covers_every_edge():
+    rnd = random.Random(0)
+    recs = []
+    for i in range(300):
+        reads = [(64 * rnd.randrange(40), 64 * rnd.randrange(40) + 64) for _ in range(2)]
+        reads = [(lo, max(hi, lo + 64)) for lo, hi in reads]
+        lo = 64 * rnd.randrange(40)
+        recs.append(_acc(reads=reads, writes=[(lo, lo + 64)]))
+    d = dag.build(recs)
+    for k in (1, 2, 5):
+        stream_of, waits = dag.assign_streams(d, [1.0] * d.n, k)
+        last = {}
+        for i in range(d.n):
+            for p in d.preds[i]:
+                assert stream_of[p] == stream_of[i] or p in waits[i]
+            assert 0 <= stream_of[i] < k
+            last[stream_of[i]] = i
+        if k == 1:
+            assert not any(waits)
+
+
+@pytest.fixture()
+def cpu_train(monkeypatch):
+    import hgb200.train as tr
+    monkeypatch.setattr(tr, "ops", fake_ops)
+    monkeypatch.setattr(tr, "_TEST_ALLOW_CPU", True)
+    monkeypatch.setattr(tr, "STREAMS", 6)
+    return tr
+
+
+def _random_topological_order(d, rnd):
+    indeg = [len(p) for p in d.preds]
+    ready = [i for i in range(d.n) if indeg[i] == 0]
+    order = []
+    while ready:
+        i = ready.pop(rnd.randrange(len(ready)))
+        order.append(i)
+        for s in d.succs[i]:
+            indeg[s] -= 1
+            if indeg[s] == 0:
+                ready.append(s)
+    assert len(order) == d.n
+    return order
+
+
+@pytest.mark.parametrize("S,J,B,H,W", [(2, 16, 2, 64, 64), (1, 17, 1, 64, 128)])
+def test_random_topological_orders_give_identical_steps(cpu_train, S, J, B, H, W):
+    from src.models import hg
+    sd = make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, seed=0)
+    model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum")
+    model.load_state_dict(sd)
+    model.train()
+    eng = cpu_train.TrainEngine(model, "cpu")
+    plan = eng.plan_for(B, H, W)
+    x, tg, tw = train_inputs(1, B, J, H, W, 1)[0]
+    plan.input.copy_(x)
+    plan.target.copy_(tg)
+    plan.target_weight.copy_(tw.reshape(B, J))
+    bns = [(b.rm, b.rv, b.nbt) for b in eng._bns]
+    keep = [tuple(t.clone() for t in b) for b in bns]
+
+    def snapshot():
+        return [eng.store.G.clone(), plan.loss.clone()] + [o.clone() for o in plan.outputs] + \
+               [t.clone() for b in bns for t in b]
+
+    def restore():
+        for b, k in zip(bns, keep):
+            for t, kt in zip(b, k):
+                t.copy_(kt)
+
+    fns = plan.launches("step")
+    for fn in fns:
+        fn()
+    want = snapshot()
+    d, stream_of, waits = plan.schedule("step")
+    assert d.n == len(fns) == len(plan.meta)
+    assert len(set(stream_of)) > 1                      # the step really has parallel branches
+    # weight gradients are leaves: most launches of the backward pass are off the critical chain
+    depth = [0] * d.n
+    for i in range(d.n):
+        depth[i] = 1 + max((depth[p] for p in d.preds[i]), default=0)
+    assert max(depth) < 0.8 * d.n
+    for seed in range(3):
+        restore()
+        order = _random_topological_order(d, random.Random(seed))
+        assert d.check_order(order)
+        for i in order:
+            fns[i]()
+        got = snapshot()
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+    # the separately captured halves (autograd drop-in) carry their own DAGs
+    for which in ("fwd", "bwd"):
+        dd, so, _ = plan.schedule(which)
+        assert dd.n == len(plan.launches(which))
