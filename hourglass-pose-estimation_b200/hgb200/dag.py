@@ -29,7 +29,7 @@ _WRITES: Dict[str, Tuple[Tuple, Tuple]] = {
     # name: (written positional indices, written keyword names)
     "conv_nhwc": ((), ("out", "out_nchw_f32")),
     "conv3x3_halo": ((), ("out",)),
-    "dwconv3x3_halo": ((), ("out",)),
+    "dwconv3x3": ((), ("out",)),
     "stem_im2col": ((), ("out",)),
     "maxpool2x2": ((1,), ("out",)),
     "colstats": ((1, 2), ("sum_out", "sumsq_out")),

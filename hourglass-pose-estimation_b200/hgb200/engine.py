@@ -198,7 +198,15 @@ class HourglassEngine:
 
         def block(bw: BlockWeights, x, up_low=None):
             bn_, bh_, bw_, _ = x.shape
-            if (bw_ >= halo_min_w and bw_ <= 128 and 128 % bw_ == 0 and (bh_ * bw_) % 128 == 0
+            if bw.depthwise:
+                # mobile=True: K2 is a depthwise 3x3 stencil on CUDA cores (9 MAC/element, HBM-bound)
+                a2 = conv(x, bw.w1, bw.b1, ksize=1, cout=bw.planes, relu=True, in_scale=bw.s1, in_shift=bw.t1)
+                a3 = arena.get((bn_, bh_, bw_, bw.planes))
+                plan.meta.append(dict(op=f"dwconv3x3_c{bw.planes}_{bh_}x{bw_}", kind="bw",
+                                      flops=2.0 * bn_ * bh_ * bw_ * 9 * bw.planes, bytes=a2.numel() * 4))
+                L.append(lambda: ops.dwconv3x3(a2, bw.w2, bw.b2, relu=True, out=a3))
+                arena.put(a2)
+            elif (bw_ >= halo_min_w and bw_ <= 128 and 128 % bw_ == 0 and (bh_ * bw_) % 128 == 0
                     and bw.planes in (64, 128) and x.shape[3] <= 512):
                 # K1 writes the halo-padded layout; K2 reads every input pixel once (hg_conv3x3.cu)
                 a2h = arena.get_halo(bn_, bh_, bw_, bw.planes)
@@ -243,18 +251,28 @@ class HourglassEngine:
             L.append(lambda: ops.maxpool2x2(x, out))
             return out
 
-        def hourglass(levels, d, x):
+        def hourglass(levels, d, x, cat=None):
             """Hourglass._hour_glass_forward(n=d+1, x); x stays owned by the caller."""
             p = pool(x)
             low1 = chain(levels[d][1], p, keep_input=False)
             if d > 0:
-                low2 = hourglass(levels, d - 1, low1)
+                low2 = hourglass(levels, d - 1, low1, cat)
                 arena.put(low1)
             else:
                 low2 = chain(levels[0][3], low1, keep_input=False)
             low3 = chain(levels[d][2], low2, keep_input=False)
-            out = chain(levels[d][0], x, up_low=low3)
+            if cat is None:
+                out = chain(levels[d][0], x, up_low=low3)
+                arena.put(low3)
+                return out
+            # skip_mode='concat': grouped 1x1 over cat([up1, upsample(low3)]) as two zero-padded GEMMs (fold.py)
+            wa, ba, wb, bb = cat
+            up1 = chain(levels[d][0], x)
+            t = conv(low3, wb, bb, ksize=1, cout=wb.shape[0])
             arena.put(low3)
+            out = conv(up1, wa, ba, ksize=1, cout=wa.shape[0], up_low=t)
+            arena.put(up1)
+            arena.put(t)
             return out
 
         # ---- stem: pack to NHWC4 (+mirror for the flip half) -> windowed implicit GEMM, no im2col matrix
@@ -282,7 +300,7 @@ class HourglassEngine:
         # ---- stacks
         hm_h, hm_w = h // 4, w // 4
         for i in range(self.num_stacks):
-            y = hourglass(W.hg[i], W.depth - 1, x)
+            y = hourglass(W.hg[i], W.depth - 1, x, W.concat[i] if W.concat else None)
             y = chain(W.res[i], y, keep_input=False)
             fw, fb = W.fc[i]
             y2 = conv(y, fw, fb, ksize=1, cout=256, relu=True)

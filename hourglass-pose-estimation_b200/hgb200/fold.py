@@ -70,8 +70,8 @@ class BlockWeights:
 
     def __init__(self, sd, p: str):
         w2 = sd[p + ".conv2.weight"]
-        if w2.shape[1] == 1 and w2.shape[0] > 1:
-            raise NotImplementedError("mobile=True (depthwise conv2) is not built into the sm_100a path yet")
+        # mobile=True: conv2 is depthwise (groups=planes, weight [planes,1,3,3]; src/models/modules.py:15-17)
+        self.depthwise = w2.shape[1] == 1 and w2.shape[0] > 1
         self.cin = sd[p + ".conv1.weight"].shape[1]
         self.planes = sd[p + ".conv1.weight"].shape[0]
         self.cout = sd[p + ".conv3.weight"].shape[0]
@@ -79,7 +79,10 @@ class BlockWeights:
         w, b = fold_bn_after_conv(sd, p + ".conv1", p + ".bn2")
         self.w1, self.b1 = gemm_weight(w), pad_bias(b)
         w, b = fold_bn_after_conv(sd, p + ".conv2", p + ".bn3")
-        self.w2, self.b2 = gemm_weight(w), pad_bias(b)
+        if self.depthwise:
+            self.w2, self.b2 = w.reshape(-1).contiguous(), b.contiguous()      # fp32 [c][9] for the CUDA-core stencil
+        else:
+            self.w2, self.b2 = gemm_weight(w), pad_bias(b)
         w, b = fold_bn_after_conv(sd, p + ".conv3", None)
         self.downsample = (p + ".downsample.0.weight") in sd
         if self.downsample:
@@ -89,6 +92,23 @@ class BlockWeights:
         else:
             self.w3 = gemm_weight(w)
         self.b3 = pad_bias(b)
+
+
+def concat_weights(w4: torch.Tensor, b: torch.Tensor):
+    """skip_mode='concat' (src/models/modules.py:58-61,91-93): conv1x1(cat([up1, up2]), groups=2) with weight
+    [2p, 2p, 1, 1] -- output channels [0,p) read up1, [p,2p) read up2 = upsample(low3).  A 1x1 convolution commutes
+    with nearest upsampling, so the layer is two zero-padded 2p->2p GEMMs on the existing kernels:
+        T   = [0 ; W_b] low3 + [0 ; b_b]            (at low resolution)
+        out = [W_a ; 0] up1 + [b_a ; 0] + upsample(T)   (the upsample-add epilogue)
+    Returns (Wa_pad, ba_pad, Wb_pad, bb_pad) in GEMM layout."""
+    co, ci = w4.shape[0], w4.shape[1]
+    half = co // 2
+    w = w4[:, :, 0, 0]
+    wa, wb = torch.zeros_like(w), torch.zeros_like(w)
+    wa[:half], wb[half:] = w[:half], w[half:]
+    ba, bb = torch.zeros_like(b), torch.zeros_like(b)
+    ba[:half], bb[half:] = b[:half], b[half:]
+    return (gemm_weight(wa[:, :, None, None]), pad_bias(ba), gemm_weight(wb[:, :, None, None]), pad_bias(bb))
 
 
 def chain_weights(sd, p: str):
@@ -107,8 +127,6 @@ class NetWeights:
 
     def __init__(self, sd: Dict[str, torch.Tensor], depth: int = 4):
         sd = {k: v.detach() for k, v in sd.items()}
-        if any(k.endswith("concat_conv.weight") for k in sd):
-            raise NotImplementedError("skip_mode='concat' is not built into the sm_100a path yet")
         self.depth = depth
         self.num_stacks = 0
         while f"score.{self.num_stacks}.weight" in sd:
@@ -121,7 +139,11 @@ class NetWeights:
         self.layer2 = chain_weights(sd, "layer2")
         self.layer3 = chain_weights(sd, "layer3")
         self.hg, self.res, self.fc, self.score, self.remap = [], [], [], [], []
+        self.concat = []
         for i in range(self.num_stacks):
+            if f"hg.{i}.concat_conv.weight" in sd:
+                self.concat.append(concat_weights(sd[f"hg.{i}.concat_conv.weight"].float(),
+                                                  sd[f"hg.{i}.concat_conv.bias"].float()))
             levels = []
             for d in range(depth):
                 levels.append([chain_weights(sd, f"hg.{i}.hg.{d}.{k}") for k in range(4 if d == 0 else 3)])

@@ -408,6 +408,31 @@ def bn_bwd_apply(dz: torch.Tensor, x: torch.Tensor, saved: torch.Tensor, sums: t
     return out
 
 
+def dwconv3x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], *, relu: bool = False, flip: bool = False,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Depthwise 3x3 / pad 1 on NHWC bf16 (hg_dwconv3x3_nhwc); weight fp32 [c*9] in torch's [c,1,3,3] order.
+    flip=True applies the reversed taps (the input gradient)."""
+    _require_cuda(x, weight, bias, out)
+    n, h, w, c = x.shape
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.float32 or weight.numel() < c * 9:
+        raise HgError("dwconv3x3: x must be bf16 NHWC and weight fp32 with c*9 elements")
+    if out is None:
+        out = torch.empty_like(x)
+    lib.check(lib.hg_dwconv3x3_nhwc(_ptr(x), _ptr(weight), _ptr(bias), _ptr(out), n, h, w, c, int(relu), int(flip), _stream()),
+              "hg_dwconv3x3_nhwc")
+    return out
+
+
+def dwconv3x3_wgrad(dout: torch.Tensor, z: torch.Tensor, dw: torch.Tensor) -> torch.Tensor:
+    """dw (fp32 [c*9], accumulated) += per-channel correlation of dout with the 3x3 neighbourhood of z."""
+    _require_cuda(dout, z, dw)
+    n, h, w, c = z.shape
+    if dout.shape != z.shape or dw.dtype != torch.float32 or dw.numel() < c * 9:
+        raise HgError("dwconv3x3_wgrad: shapes differ or dw too small")
+    lib.check(lib.hg_dwconv3x3_wgrad(_ptr(dout), _ptr(z), _ptr(dw), n, h, w, c, _stream()), "hg_dwconv3x3_wgrad")
+    return dw
+
+
 def maxpool2x2_bwd(x: torch.Tensor, dpool: torch.Tensor, dx: torch.Tensor, accumulate: bool):
     _require_cuda(x, dpool, dx)
     n, h, w, c = x.shape

@@ -207,6 +207,18 @@ int hg_bn_bwd_apply(const void* dz, const void* x, const float* saved, const flo
                     const void* add2, void* out, float* dgamma, float* dbeta, int32_t n, int32_t h, int32_t w, int32_t c,
                     int32_t out_halo, int32_t relu, void* stream);
 
+/* Depthwise 3x3, stride 1, zero padding 1 (mobile=True bottlenecks: nn.Conv2d(planes, planes, 3, padding=1,
+ * groups=planes), src/models/modules.py:15-17) on NHWC bf16 [n][h][w][c]; w: fp32 [c][9] (torch's [c,1,3,3]
+ * memory), bias fp32 [c] or NULL; out = (relu?)(conv + bias) rounded once to bf16.  flip_taps != 0 applies the
+ * taps reversed: the convolution's input gradient.  c/8 must be a power of two <= 32.  CUDA-core stencil,
+ * HBM-bound (9 MAC per element). */
+int hg_dwconv3x3_nhwc(const void* x, const float* w, const float* bias, void* out, int32_t n, int32_t h, int32_t w_,
+                      int32_t c, int32_t relu, int32_t flip_taps, void* stream);
+/* Weight gradient of the depthwise 3x3: dw[c][tap] += sum over pixels dout[p][c] * z[p + tap][c] (fp32 [c][9],
+ * accumulated into what is there). */
+int hg_dwconv3x3_wgrad(const void* dout, const void* z, float* dw, int32_t n, int32_t h, int32_t w_, int32_t c,
+                       void* stream);
+
 /* F.max_pool2d(x,2,2) backward: dx (+)= dpool routed to the first maximum of each window (torch's rule).
  * With accumulate == 0 every element of dx is written.  src/models/modules.py:82, hourglass.py:76. */
 int hg_maxpool2x2_bwd_nhwc(const void* x, const void* dpool, void* dx, int32_t n, int32_t h, int32_t w, int32_t c,

@@ -18,29 +18,26 @@ GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 HEATMAP_TOL = 2e-2
 
 
-def _build(S, J, nb=1, seed=0):
+def _build(S, J, nb=1, seed=0, mobile=False, concat=False):
     from src.models import hg
-    sd = make_state_dict(num_stacks=S, num_blocks=nb, num_classes=J, seed=seed)
-    model = hg(num_stacks=S, num_blocks=nb, num_classes=J, mobile=False, skip_mode='sum', out_res=64)
+    skip = 'concat' if concat else 'sum'
+    sd = make_state_dict(num_stacks=S, num_blocks=nb, num_classes=J, mobile=mobile, skip_mode=skip, seed=seed)
+    model = hg(num_stacks=S, num_blocks=nb, num_classes=J, mobile=mobile, skip_mode=skip, out_res=64)
     model.load_state_dict(sd, strict=True)
     return sd, model.to("cuda:0").eval()
 
 
 def _golden_cases():
-    out = []
-    for p in sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz"))):
-        cfg = np.load(p)["cfg"]
-        if int(cfg[6]) or int(cfg[7]):          # mobile / concat variants: not on the sm_100a path yet
-            continue
-        out.append(p)
-    return out
+    # six configurations run through the live reference (oracle/make_golden.py), incl. mobile=True (depthwise conv2)
+    # and skip_mode='concat' 
+    return sorted(glob.glob(os.path.join(GOLDEN, "model_*.npz")))
 
 
 @pytest.mark.parametrize("path", _golden_cases(), ids=lambda p: os.path.basename(p)[:-4])
 def test_forward_matches_reference_golden(path):
     z = np.load(path)
     S, J, B, H, W, seed, mobile, concat, nb = [int(v) for v in z["cfg"]]
-    sd, model = _build(S, J, nb, seed)
+    sd, model = _build(S, J, nb, seed, bool(mobile), bool(concat))
     x = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(seed + 1000))
     with torch.no_grad():
         outs = model(x.cuda())

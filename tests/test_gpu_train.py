@@ -141,6 +141,32 @@ def test_batchnorm_train_forward_backward(n, h, w, c, halo):
         assert bool((full == 0).all())
 
 
+@pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 128), (3, 4, 4, 128), (1, 64, 48, 64), (2, 7, 5, 64), (33, 2, 2, 128),
+                                     (1, 1, 1, 64), (2, 128, 128, 64), (1, 9, 3, 256)])
+def test_depthwise_3x3_forward_dgrad_wgrad(n, h, w, c):
+    """hg_dwconv3x3_nhwc / hg_dwconv3x3_wgrad (mobile=True bottlenecks, modules.py:15-17) against torch fp32."""
+    from hgb200 import ops
+    g = torch.Generator().manual_seed(h * w + c)
+    x = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).cuda()
+    wt = (torch.randn(c, 1, 3, 3, generator=g) / 3).cuda()
+    b = torch.randn(c, generator=g).cuda()
+    xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wp = wt.clone().requires_grad_(True)
+    ref = F.conv2d(xf, wp, b, padding=1, groups=c)
+    out = ops.dwconv3x3(x, wt.reshape(-1), b)
+    assert torch.equal(out.float().permute(0, 3, 1, 2), r16(ref.detach())) or rel(out.float().permute(0, 3, 1, 2), ref.detach()) < 5e-3
+    out_r = ops.dwconv3x3(x, wt.reshape(-1), b, relu=True)
+    assert rel(out_r.float().permute(0, 3, 1, 2), F.relu(ref.detach())) < 5e-3
+    dy = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).cuda()
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dx = ops.dwconv3x3(dy, wt.reshape(-1), None, flip=True)
+    assert rel(dx.float().permute(0, 3, 1, 2), xf.grad) < 5e-3
+    dw = torch.full((c * 9,), 0.25, device="cuda")           # accumulates into what is there
+    ops.dwconv3x3_wgrad(dy, x, dw)
+    torch.cuda.synchronize()
+    assert rel(dw.view(c, 1, 3, 3), 0.25 + wp.grad) < 1e-4
+
+
 @pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 256), (3, 4, 6, 64), (1, 64, 48, 128)])
 def test_pool_upsample_backward_and_add(n, h, w, c):
     from hgb200 import ops
