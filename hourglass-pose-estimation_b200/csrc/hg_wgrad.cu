@@ -56,7 +56,7 @@ struct Params {
     int stages;
     int ld;                 // floats between consecutive co rows of dW
     int tap_stride;         // floats between taps inside a dW row
-    int co_valid, ci_valid;
+    int co_first, co_valid, ci_valid;      // rows [co_first, co_valid) of dout^T.z are written, to dW rows 0..
     int vec4;               // dW rows / taps are 16-byte aligned: use red.v4
     int tmem_cols;
     uint32_t lbo_a, sbo_a, lbo_b, sbo_b;   // MN-major descriptor byte offsets
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
                 const int co = h * 128 + q * 32 + lane;
                 for (int t = 0; t < p.taps_per_cta; ++t) {
                     const int tap = group * p.taps_per_cta + t;
-                    float* dst = p.dw + static_cast<long long>(co) * p.ld + static_cast<long long>(tap) * p.tap_stride;
+                    float* dst = p.dw + static_cast<long long>(co - p.co_first) * p.ld + static_cast<long long>(tap) * p.tap_stride;
                     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                            static_cast<uint32_t>((h * p.taps_per_cta + t) * N);
                     for (int c0 = 0; c0 < N; c0 += 32) {
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
                         uint32_t v[32];
                         tmem_ld_32x32(t_row + c0, v);
                         tmem_ld_wait();
-                        if (co < p.co_valid) {
+                        if (co >= p.co_first && co < p.co_valid) {
                             if (p.vec4) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i)
@@ -257,13 +257,13 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t r
 }  // namespace hg
 
 extern "C" int hg_wgrad_bf16(const void* dout, const void* z, float* dw, unsigned int* err_word, int64_t rows, int32_t co,
-                             int32_t co_valid, int32_t ci, int32_t ci_valid, int32_t taps, int32_t halo_pitch, int32_t ld,
+                             int32_t co_first, int32_t co_valid, int32_t ci, int32_t ci_valid, int32_t taps, int32_t halo_pitch, int32_t ld,
                              int32_t tap_stride, void* stream) {
     using namespace hg;
     using namespace hg::wg;
     if (!dout || !z || !dw || rows <= 0 || rows > 0x7fffff00LL || co <= 0 || co > 256 || ci <= 0 || ci > 256 ||
         co % 8 != 0 || ci % 64 != 0 || (taps != 1 && taps != 9) || (taps == 9 && halo_pitch < 2) || ci_valid <= 0 ||
-        ci_valid > ci || co_valid <= 0 || co_valid > co) {
+        ci_valid > ci || co_valid <= 0 || co_valid > co || co_first < 0 || co_first >= co_valid) {
         set_last_error("hg_wgrad_bf16: bad arguments (co<=256 multiple of 8, ci<=256 multiple of 64, taps 1|9)");
         return HG_ERR_INVALID;
     }
@@ -280,6 +280,7 @@ extern "C" int hg_wgrad_bf16(const void* dout, const void* z, float* dw, unsigne
     kp.b_rows = taps == 9 ? 72 : 64;
     kp.ld = ld;
     kp.tap_stride = tap_stride;
+    kp.co_first = co_first;
     kp.co_valid = co_valid;
     kp.ci_valid = ci_valid;
     kp.vec4 = (ld % 4 == 0 && tap_stride % 4 == 0 && ci_valid % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0) ? 1 : 0;

@@ -344,13 +344,14 @@ def jmse_loss(preds: Sequence[torch.Tensor], target: Optional[torch.Tensor], tar
 
 
 # ------------------------------------------------------------------------------------------------ training
-def wgrad(dout: torch.Tensor, z: torch.Tensor, dw: torch.Tensor, *, co_valid: Optional[int] = None,
+def wgrad(dout: torch.Tensor, z: torch.Tensor, dw: torch.Tensor, *, co_valid: Optional[int] = None, co_first: int = 0,
           ci_valid: Optional[int] = None, taps: int = 1, halo_pitch: int = 0, ld: Optional[int] = None,
           tap_stride: Optional[int] = None) -> torch.Tensor:
     """dw (fp32, pre-zeroed or partial) += dout^T . z over rows (hg_wgrad_bf16).
 
     dout: bf16 [..., co], z: bf16 [..., ci] with the same number of rows (taps=9: both halo-padded flat
-    buffers incl. the leading zero row).  dw rows are `ld` floats apart, taps `tap_stride` apart."""
+    buffers incl. the leading zero row).  dw rows are `ld` floats apart, taps `tap_stride` apart; only dout's
+    channels [co_first, co_valid) are written (to dw rows 0..co_valid-co_first-1)."""
     _require_cuda(dout, z, dw)
     if dout.dtype != torch.bfloat16 or z.dtype != torch.bfloat16 or dw.dtype != torch.float32:
         raise HgError("wgrad: dout/z must be bf16, dw fp32")
@@ -362,9 +363,9 @@ def wgrad(dout: torch.Tensor, z: torch.Tensor, dw: torch.Tensor, *, co_valid: Op
     co_valid = co if co_valid is None else co_valid
     tap_stride = ci_valid if tap_stride is None else tap_stride
     ld = taps * tap_stride if ld is None else ld
-    if dw.numel() < (co_valid - 1) * ld + (taps - 1) * tap_stride + ci_valid:
+    if dw.numel() < (co_valid - co_first - 1) * ld + (taps - 1) * tap_stride + ci_valid:
         raise HgError("wgrad: dw too small")
-    lib.check(lib.hg_wgrad_bf16(_ptr(dout), _ptr(z), _ptr(dw), _ptr(err_word(dout.device)), rows, co, co_valid, ci,
+    lib.check(lib.hg_wgrad_bf16(_ptr(dout), _ptr(z), _ptr(dw), _ptr(err_word(dout.device)), rows, co, co_first, co_valid, ci,
                                 ci_valid, taps, halo_pitch, ld, tap_stride, _stream()), "hg_wgrad_bf16")
     return dw
 

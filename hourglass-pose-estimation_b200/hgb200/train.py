@@ -145,9 +145,11 @@ class _Conv:
         st = eng.store
         wname, bname = eng.pname[id(conv.weight)], eng.pname[id(conv.bias)]
         co, ci, kh, kw = conv.weight.shape
-        if conv.groups != 1:
-            raise NotImplementedError("mobile=True / skip_mode='concat' (grouped convolutions) are not on the sm_100a "
-                                      "training path yet")
+        # mobile=True: conv2 is depthwise (src/models/modules.py:15-17) -- a CUDA-core stencil straight on the fp32
+        # master weights ([c][3][3][1] in the flat store = the kernel's [c][9]); no bf16 GEMM copies
+        self.depthwise = conv.groups > 1 and conv.groups == conv.in_channels == co and (kh, kw) == (3, 3)
+        if conv.groups != 1 and not self.depthwise:
+            raise HgError(f"grouped convolution (groups={conv.groups}) outside the depthwise / concat_conv cases")
         self.co, self.ci, self.taps = co, ci, kh * kw
         self.row_len = self.taps * ci
         self.w, self.gw = st.flat(st.P, wname), st.flat(st.G, wname)
@@ -155,6 +157,9 @@ class _Conv:
         self.b = st.flat(st.P, bname, extra=co_pad - co)      # padded view (tail of P is padded)
         self.gb = st.flat(st.G, bname)
         dev = st.device
+        if self.depthwise:
+            self.wf = self.wd = None
+            return
         if fwd_into is not None:
             self.wf, col0, ld = fwd_into
         else:
@@ -191,6 +196,37 @@ class _Bn:
 class _Block:
     """One HGBottleneck (src/models/modules.py:6-47): filled in by TrainEngine._block()."""
     __slots__ = ("cin", "planes", "cout", "bn1", "bn2", "bn3", "c1", "c2", "c3", "ds", "wf3", "b3")
+
+
+class _Concat:
+    """skip_mode='concat' (src/models/modules.py:58-61,91-93): conv1x1(cat([up1, upsample(low3)]), groups=2), ONE conv
+    shared by the four levels of a stack's Hourglass.  Output channels [0,p) read up1, [p,2p) read low3; a 1x1
+    convolution commutes with nearest upsampling, so it runs as two zero-padded 2p->2p GEMMs on the existing kernels:
+    T = [0;W_b] low3 + [0;b_b] at low resolution, out = [W_a;0] up1 + [b_a;0] + upsample(T) (upsample-add epilogue)."""
+
+    def __init__(self, eng: "TrainEngine", conv: nn.Conv2d):
+        st = eng.store
+        dev = st.device
+        wname, bname = eng.pname[id(conv.weight)], eng.pname[id(conv.bias)]
+        co, cig = conv.weight.shape[0], conv.weight.shape[1]
+        if conv.groups != 2 or conv.kernel_size != (1, 1) or co % 2:
+            raise HgError("concat_conv: expected a 1x1 convolution with groups=2")
+        self.co, self.cig, self.half = co, cig, co // 2
+        h = self.half
+        self.w, self.gw = st.flat(st.P, wname), st.flat(st.G, wname)          # [co][cig]
+        self.b, self.gb = st.flat(st.P, bname), st.flat(st.G, bname)
+        self.wfa = torch.zeros((co, cig), dtype=_ACT, device=dev)
+        self.wfb = torch.zeros((co, cig), dtype=_ACT, device=dev)
+        self.wda = torch.zeros((cig, co), dtype=_ACT, device=dev)
+        self.wdb = torch.zeros((cig, co), dtype=_ACT, device=dev)
+        self.ba = torch.zeros(co, dtype=torch.float32, device=dev)
+        self.bb = torch.zeros(co, dtype=torch.float32, device=dev)
+        eng.pack_entries.append(dict(src=self.w[:h * cig], dst_fwd=self.wfa, dst_dgrad=self.wda, co=h, taps=1, ci=cig,
+                                     fwd_ld=cig, fwd_col0=0, dgrad_ld=co))
+        eng.pack_entries.append(dict(src=self.w[h * cig:], dst_fwd=self.wfb[h:], dst_dgrad=self.wdb[:, h:], co=h, taps=1,
+                                     ci=cig, fwd_ld=cig, fwd_col0=0, dgrad_ld=co))
+        eng.pack_entries.append(dict(src=self.b[:h], dst_f32=self.ba, co=h, taps=1, ci=1))
+        eng.pack_entries.append(dict(src=self.b[h:], dst_f32=self.bb[h:], co=h, taps=1, ci=1))
 
 
 class _Remap:
@@ -268,7 +304,7 @@ def _describe(name, a, k):
         nbytes = _nbytes(dout, z) + co * z.shape[-1] * taps * 4
         tag = f"wgrad_co{dout.shape[-1]}_ci{z.shape[-1]}_t{taps}_rows{rows}"
     elif name in ("colstats", "bn_train_fwd", "bn_bwd_reduce", "bn_bwd_apply", "maxpool2x2", "maxpool2x2_bwd", "sumpool2x2",
-                  "add_inplace", "nchw_to_nhwc_bf16_pad", "stem_im2col"):
+                  "add_inplace", "nchw_to_nhwc_bf16_pad", "stem_im2col", "dwconv3x3", "dwconv3x3_wgrad"):
         big = [t for t in list(a) + list(k.values()) if torch.is_tensor(t) and t.numel() > 4096]
         nbytes = _nbytes(*big)
         ref = big[0] if big else None
@@ -435,8 +471,9 @@ class TrainEngine:
         self.layer1 = [self._block(m) for m in model.layer1]
         self.layer2 = [self._block(m) for m in model.layer2]
         self.layer3 = [self._block(m) for m in model.layer3]
-        self.hg, self.res, self.fc, self.score, self.remap = [], [], [], [], []
+        self.hg, self.res, self.fc, self.score, self.remap, self.concat = [], [], [], [], [], []
         for i in range(self.num_stacks):
+            self.concat.append(_Concat(self, model.hg[i].concat_conv) if hasattr(model.hg[i], "concat_conv") else None)
             levels = []
             for d in range(self.depth):
                 levels.append([[self._block(m) for m in chain] for chain in model.hg[i].hg[d]])
@@ -518,15 +555,19 @@ class TrainEngine:
             pl = blk.planes
             z1 = new((nb, hh_, ww_, cin))
             a1 = new((nb, hh_, ww_, pl))
-            z2h = new_halo(nb, hh_, ww_, pl)
+            z2h = new((nb, hh_, ww_, pl)) if blk.c2.depthwise else new_halo(nb, hh_, ww_, pl)
             a2 = new((nb, hh_, ww_, pl))
             z3 = new((nb, hh_, ww_, pl))
             y = _T(new((nb, hh_, ww_, blk.cout)))
             xd = x.data
             bn_fwd(blk.bn1, xd, z1)
             F.append(lambda: ops.conv_nhwc(z1, blk.c1.wf, blk.c1.b, ksize=1, cout=pl, out=a1))
-            bn_fwd(blk.bn2, a1, z2h, halo=True)
-            F.append(lambda: ops.conv3x3_halo(z2h, blk.c2.wf, blk.c2.b, n=nb, h=hh_, w=ww_, cin=pl, cout=pl, out=a2))
+            if blk.c2.depthwise:
+                bn_fwd(blk.bn2, a1, z2h)
+                F.append(lambda: ops.dwconv3x3(z2h, blk.c2.w, blk.c2.b, out=a2))
+            else:
+                bn_fwd(blk.bn2, a1, z2h, halo=True)
+                F.append(lambda: ops.conv3x3_halo(z2h, blk.c2.wf, blk.c2.b, n=nb, h=hh_, w=ww_, cin=pl, cout=pl, out=a2))
             bn_fwd(blk.bn3, a2, z3)
             lowd = up_low.data if up_low is not None else None
             if blk.ds is not None:
@@ -550,12 +591,20 @@ class TrainEngine:
             nodes.append(dict(kind="pool", x=x, y=p))
             return p
 
-        def hourglass(levels, d, x: _T) -> _T:
+        def hourglass(levels, d, x: _T, cat: Optional[_Concat]) -> _T:
             p = pool(x)
             low1 = chain(levels[d][1], p)
-            low2 = hourglass(levels, d - 1, low1) if d > 0 else chain(levels[0][3], low1)
+            low2 = hourglass(levels, d - 1, low1, cat) if d > 0 else chain(levels[0][3], low1)
             low3 = chain(levels[d][2], low2)
-            return chain(levels[d][0], x, up_low=low3)
+            if cat is None:
+                return chain(levels[d][0], x, up_low=low3)
+            up1 = chain(levels[d][0], x)
+            t = new(low3.data.shape)
+            y = _T(new(x.data.shape))
+            F.append(lambda: ops.conv_nhwc(low3.data, cat.wfb, cat.bb, ksize=1, cout=cat.co, out=t))
+            F.append(lambda: ops.conv_nhwc(up1.data, cat.wfa, cat.ba, ksize=1, cout=cat.co, up_low=t, out=y.data))
+            nodes.append(dict(kind="concat", cat=cat, up1=up1, low3=low3, y=y))
+            return y
 
         # ---- stem: im2col rows (kept: they are the stem's wgrad operand) -> GEMM -> BN+ReLU
         rows = new((n, h // 2, w // 2, 192))
@@ -571,7 +620,7 @@ class TrainEngine:
         x = chain(self.layer3, l2)
         J = self.num_classes
         for i in range(self.num_stacks):
-            y = hourglass(self.hg[i], self.depth - 1, x)
+            y = hourglass(self.hg[i], self.depth - 1, x, self.concat[i])
             y = chain(self.res[i], y)
             fcc, fcb = self.fc[i]
             nb, hh_, ww_, ch = y.data.shape
@@ -646,15 +695,24 @@ class TrainEngine:
                     B.append(lambda gy=gy, blk=blk, xd=x.data: ops.wgrad(gy, xd, blk.ds.gw))
                 dz3 = arena.get((nb, hh_, ww_, pl))
                 dgrad1x1(gy, blk.c3.wd, pl, dz3)
-                da2h = arena.get_halo(nb, hh_, ww_, pl)
-                bn_bwd(blk.bn3, dz3, node["a2"], da2h, halo=True)
-                arena.put(dz3)
-                B.append(lambda da2h=da2h, z2h=node["z2h"], blk=blk, P=ww_ + 1, pl=pl:
-                         ops.wgrad(da2h.view(-1, pl), z2h.view(-1, pl), blk.c2.gw, taps=9, halo_pitch=P))
-                dz2 = arena.get((nb, hh_, ww_, pl))
-                B.append(lambda da2h=da2h, blk=blk, dz2=dz2, nb=nb, hh_=hh_, ww_=ww_, pl=pl:
-                         ops.conv3x3_halo(da2h, blk.c2.wd, None, n=nb, h=hh_, w=ww_, cin=pl, cout=pl, out=dz2))
-                arena.put_halo(da2h, nb, hh_, ww_, pl)
+                if blk.c2.depthwise:
+                    da2 = arena.get((nb, hh_, ww_, pl))
+                    bn_bwd(blk.bn3, dz3, node["a2"], da2)
+                    arena.put(dz3)
+                    B.append(lambda da2=da2, z2=node["z2h"], blk=blk: ops.dwconv3x3_wgrad(da2, z2, blk.c2.gw))
+                    dz2 = arena.get((nb, hh_, ww_, pl))
+                    B.append(lambda da2=da2, blk=blk, dz2=dz2: ops.dwconv3x3(da2, blk.c2.w, None, flip=True, out=dz2))
+                    arena.put(da2)
+                else:
+                    da2h = arena.get_halo(nb, hh_, ww_, pl)
+                    bn_bwd(blk.bn3, dz3, node["a2"], da2h, halo=True)
+                    arena.put(dz3)
+                    B.append(lambda da2h=da2h, z2h=node["z2h"], blk=blk, P=ww_ + 1, pl=pl:
+                             ops.wgrad(da2h.view(-1, pl), z2h.view(-1, pl), blk.c2.gw, taps=9, halo_pitch=P))
+                    dz2 = arena.get((nb, hh_, ww_, pl))
+                    B.append(lambda da2h=da2h, blk=blk, dz2=dz2, nb=nb, hh_=hh_, ww_=ww_, pl=pl:
+                             ops.conv3x3_halo(da2h, blk.c2.wd, None, n=nb, h=hh_, w=ww_, cin=pl, cout=pl, out=dz2))
+                    arena.put_halo(da2h, nb, hh_, ww_, pl)
                 da1 = arena.get((nb, hh_, ww_, pl))
                 bn_bwd(blk.bn2, dz2, node["a1"], da1)
                 arena.put(dz2)
@@ -683,6 +741,23 @@ class TrainEngine:
                         bn_bwd(blk.bn1, dz1, x.data, x.grad, add1=gy, add2=x.grad)
                         release(y)
                 arena.put(dz1)
+            elif kind == "concat":
+                cat, up1, low3, y = node["cat"], node["up1"], node["low3"], node["y"]
+                gy = y.grad
+                h_ = cat.half
+                B.append(lambda gy=gy, cat=cat: ops.colstats(gy, cat.gb))
+                B.append(lambda gy=gy, cat=cat, u=up1.data, h_=h_: ops.wgrad(gy, u, cat.gw, co_valid=h_))
+                dt = arena.get(low3.data.shape)
+                B.append(lambda gy=gy, dt=dt: ops.sumpool2x2(gy, dt, accumulate=False))
+                B.append(lambda dt=dt, cat=cat, l3=low3.data, h_=h_:
+                         ops.wgrad(dt, l3, cat.gw[h_ * cat.cig:], co_first=h_))
+                assert up1.grad is None and low3.grad is None
+                up1.grad = arena.get(up1.data.shape)
+                dgrad1x1(gy, cat.wda, cat.cig, up1.grad)
+                low3.grad = arena.get(low3.data.shape)
+                dgrad1x1(dt, cat.wdb, cat.cig, low3.grad)
+                arena.put(dt)
+                release(y)
             elif kind == "pool":
                 x, y = node["x"], node["y"]
                 acc = x.grad is not None

@@ -172,14 +172,14 @@ int hg_jmse_loss(const float* const* preds, float* const* grads, const float* ta
  * (3x3: also tap-flipped) weight copies; the entries below are the rest of the backward pass.
  * ------------------------------------------------------------------------------------------- */
 /* conv.weight.grad as a split-K tcgen05 GEMM over pixels, reading both NHWC operands as they lie
- * (MN-major UMMA descriptors):  dw[o*ld + tap*tap_stride + i] += sum_f dout[f][o] * z[f + off(tap)][i]
- * for o < co_valid, i < ci_valid.  dout: bf16 [rows][co], z: bf16 [rows][ci]; dw is fp32 and must be
+ * (MN-major UMMA descriptors):  dw[(o-co_first)*ld + tap*tap_stride + i] += sum_f dout[f][o] * z[f + off(tap)][i]
+ * for co_first <= o < co_valid, i < ci_valid (a window of dout's channels: the two groups of skip_mode='concat').  dout: bf16 [rows][co], z: bf16 [rows][ci]; dw is fp32 and must be
  * zero-initialised (or hold a partial sum): CTAs add with red.global.
  * taps == 1: off = 0.  taps == 9: both tensors are halo-padded buffers of identical geometry
  * (hg_conv3x3_halo_bf16) INCLUDING the leading zero row, rows = all positions, halo_pitch = w+1,
  * off(tap) = (tap/3-1)*halo_pitch + tap%3-1.   co <= 256 (multiple of 8), ci in {64,128,192,256}. */
 int hg_wgrad_bf16(const void* dout, const void* z, float* dw, unsigned int* err_word, int64_t rows, int32_t co,
-                  int32_t co_valid, int32_t ci, int32_t ci_valid, int32_t taps, int32_t halo_pitch, int32_t ld,
+                  int32_t co_first, int32_t co_valid, int32_t ci, int32_t ci_valid, int32_t taps, int32_t halo_pitch, int32_t ld,
                   int32_t tap_stride, void* stream);
 
 /* Per-channel sum (and sum of squares) over the pixels of an NHWC bf16 tensor, ADDED into fp32

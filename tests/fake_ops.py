@@ -56,6 +56,28 @@ def conv3x3_halo(x_halo, weight, bias, *, n, h, w, cin, cout, relu=False, out=No
     return conv_nhwc(x, weight, bias, ksize=3, cout=cout, relu=relu, out=out)
 
 
+def dwconv3x3(x, weight, bias, *, relu=False, flip=False, out=None):
+    c = x.shape[-1]
+    w4 = weight[:c * 9].float().reshape(c, 1, 3, 3)
+    if flip:
+        w4 = w4.flip(2, 3)
+    y = F.conv2d(_nchw(x), w4, bias[:c].float() if bias is not None else None, padding=1, groups=c)
+    if relu:
+        y = F.relu(y)
+    if out is None:
+        out = torch.empty_like(x)
+    return _store(out, y)
+
+
+def dwconv3x3_wgrad(dout, z, dw):
+    c = z.shape[-1]
+    g, zz = _nchw(dout), F.pad(_nchw(z), (1, 1, 1, 1))
+    h, w = g.shape[2], g.shape[3]
+    acc = torch.stack([(g * zz[:, :, ky:ky + h, kx:kx + w]).sum((0, 2, 3)) for ky in range(3) for kx in range(3)], 1)
+    dw[:c * 9] += acc.reshape(-1)
+    return dw
+
+
 def stem_im2col(x_nchw, flip_w=False, out=None):
     n, c, h, w = x_nchw.shape
     cols = F.unfold(x_nchw, 7, padding=3, stride=2)              # [n, c*49, L], row index = c*49 + ky*7 + kx
@@ -166,7 +188,7 @@ def bn_bwd_apply(dz, x, saved, sums, out, *, add1=None, add2=None, dgamma=None, 
     return out
 
 
-def wgrad(dout, z, dw, *, co_valid=None, ci_valid=None, taps=1, halo_pitch=0, ld=None, tap_stride=None):
+def wgrad(dout, z, dw, *, co_valid=None, co_first=0, ci_valid=None, taps=1, halo_pitch=0, ld=None, tap_stride=None):
     co, ci = dout.shape[-1], z.shape[-1]
     cov = co if co_valid is None else co_valid
     civ = ci if ci_valid is None else ci_valid
@@ -181,8 +203,8 @@ def wgrad(dout, z, dw, *, co_valid=None, ci_valid=None, taps=1, halo_pitch=0, ld
         lo, hi = max(0, -off), min(rows, rows - off)
         bs[lo:hi] = b[lo + off:hi + off]
         g = a.t() @ bs                                          # [co, ci]
-        view = torch.as_strided(dw, (cov, civ), (ld, 1), dw.storage_offset() + tap * tap_stride)
-        view += g[:cov, :civ]
+        view = torch.as_strided(dw, (cov - co_first, civ), (ld, 1), dw.storage_offset() + tap * tap_stride)
+        view += g[co_first:cov, :civ]
     return dw
 
 

@@ -41,10 +41,10 @@ def _no_tf32():
     torch.backends.cuda.matmul.allow_tf32 = False
 
 
-def _model(S, J, seed=0):
+def _model(S, J, seed=0, mobile=False, skip="sum"):
     from src.models import hg
-    sd = make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, seed=seed)
-    model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum")
+    sd = make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, mobile=mobile, skip_mode=skip, seed=seed)
+    model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=mobile, skip_mode=skip)
     model.load_state_dict(sd)
     return sd, model.cuda().train()
 
@@ -227,14 +227,15 @@ def test_pack_rmsprop_small_gemm_pad():
 
 
 # ------------------------------------------------------------------------------------------------ whole step
-@pytest.mark.parametrize("S,J,B,H,W", [(2, 16, 4, 128, 128), (1, 17, 2, 128, 192)])
-def test_every_launch_of_the_step_matches_the_emulation(monkeypatch, S, J, B, H, W):
+@pytest.mark.parametrize("S,J,B,H,W,mobile,skip", [(2, 16, 4, 128, 128, False, "sum"), (1, 17, 2, 128, 192, False, "sum"),
+                                                   (2, 16, 2, 128, 128, True, "sum"), (2, 14, 2, 128, 128, True, "concat")])
+def test_every_launch_of_the_step_matches_the_emulation(monkeypatch, S, J, B, H, W, mobile, skip):
     """tests/shadow_ops.py: each launch of the real step replayed by the CPU emulation on the same inputs."""
     import hgb200.train as tr
     from shadow_ops import ShadowOps
     shadow = ShadowOps(tr.ops)
     monkeypatch.setattr(tr, "ops", shadow)
-    sd, model = _model(S, J)
+    sd, model = _model(S, J, mobile=mobile, skip=skip)
     eng = tr.TrainEngine(model)
     x, tg, tw = train_inputs(1, B, J, H, W, 1)[0]
     loss = eng.train_step(x.cuda(), tg.cuda(), tw.cuda(), 2.5e-4, use_graph=False)
@@ -328,6 +329,25 @@ def test_loss_trajectory_tracks_the_oracle_and_decreases():
     assert int(model.bn1.num_batches_tracked) == steps
 
 
+@pytest.mark.parametrize("mobile,skip", [(True, "sum"), (True, "concat")])
+def test_mobile_and_concat_variants_train(mobile, skip):
+    """The shipped YAML trains mobile=True (configs/train_evaluate.yaml:15): the graph step must learn, and its first
+    loss must match the fp32 oracle's."""
+    from hgb200.train import train_engine
+    S, J, B, H, W, steps, lr = 2, 16, 4, 128, 128, 6, 2.5e-4
+    sd, model = _model(S, J, mobile=mobile, skip=skip)
+    eng = train_engine(model)
+    batch = train_inputs(1, B, J, H, W, 1)[0]
+    ref_loss, _, _ = T.forward_backward({k: v.clone() for k, v in sd.items()}, *batch)
+    x, tg, tw = batch
+    mine = [float(eng.train_step(x.cuda(), tg.cuda(), tw.cuda(), lr)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    tr_ops = __import__("hgb200.ops", fromlist=["check_err_word"])
+    tr_ops.check_err_word()
+    assert abs(mine[0] - ref_loss) <= 3e-2 * ref_loss
+    assert mine[-1] < 0.6 * mine[0]
+
+
 def test_autograd_dropin_matches_fused_step():
     """The reference's own loop -- model(x); criterion(...); optimizer.zero_grad(); loss.backward();
     optimizer.step() with torch.optim.RMSprop -- against the fused engine step, same kernels underneath."""
@@ -347,7 +367,8 @@ def test_autograd_dropin_matches_fused_step():
     loss.backward()
     g1 = torch.cat([p.grad.reshape(-1) for p in m1.parameters()])
     g2 = torch.cat([p.grad.reshape(-1) for p in m2.parameters()])
-    assert abs(float(loss) - loss2) <= 2e-3 * loss2                 # BN sums are atomics: run-to-run order noise only
+    # BN sums are fp32 atomics: two runs of the SAME path differ by 0.4-1 % in loss (profiles/r1_train_dag_check.log)
+    assert abs(float(loss.detach()) - loss2) <= 2e-2 * loss2
     assert float((g1 - g2).norm() / g2.norm()) < 0.2
     opt.step()
     d = torch.cat([(a - b).abs().reshape(-1) for a, b in zip(m1.parameters(), m2.parameters())])

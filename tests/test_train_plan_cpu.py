@@ -35,16 +35,18 @@ def _grad_report(model, ref_grads):
     return rows
 
 
-@pytest.mark.parametrize("S,J,B,H,W", [(2, 16, 4, 128, 128), (1, 17, 3, 64, 128)])
-def test_plan_is_exact_with_fp32_storage(cpu_train, monkeypatch, S, J, B, H, W):
+@pytest.mark.parametrize("S,J,B,H,W,mobile,skip", [(2, 16, 4, 128, 128, False, "sum"), (1, 17, 3, 64, 128, False, "sum"),
+                                                   (2, 16, 2, 128, 128, True, "sum"), (1, 16, 4, 128, 128, False, "concat"),
+                                                   (1, 14, 4, 128, 128, True, "concat")])
+def test_plan_is_exact_with_fp32_storage(cpu_train, monkeypatch, S, J, B, H, W, mobile, skip):
     """With activations and GEMM weights stored in fp32 the plan IS the reference's step: every gradient must
     match the oracle to accumulation-order noise.  (bf16 storage is the product's numeric type; its noise is
     measured against a stock-PyTorch bf16 yardstick in tests/test_gpu_train.py.)"""
     from src.models import hg
     monkeypatch.setattr(cpu_train, "_ACT", torch.float32)
     monkeypatch.setattr(fake_ops, "BF", torch.float32)
-    sd = make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, seed=0)
-    model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum")
+    sd = make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, mobile=mobile, skip_mode=skip, seed=0)
+    model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=mobile, skip_mode=skip)
     model.load_state_dict(sd)
     model.train()
     eng = cpu_train.TrainEngine(model, "cpu")
