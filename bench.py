@@ -302,6 +302,17 @@ def run_train(args):
         fin[i] = per[i] + max((fin[q] for q in d.preds[i]), default=0.0)
     dag_info = {"streams": _tr.STREAMS, "launch_closures": d.n, "edges": sum(len(q) for q in d.preds),
                 "cross_stream_edges": sum(len(q) for q in waits), "sum_of_launch_ms": total_ms, "critical_path_ms": max(fin)}
+    # walk the critical chain back from its end: which kernel classes it is made of
+    crit = {}
+    i = max(range(d.n), key=lambda j: fin[j])
+    while True:
+        c = crit.setdefault(plan.meta[i]["op"], [0, 0.0])
+        c[0] += 1
+        c[1] += per[i]
+        if not d.preds[i]:
+            break
+        i = max(d.preds[i], key=lambda j: fin[j])
+    dag_info["critical_path_launches"] = sum(c[0] for c in crit.values())
     top_name, top = max(classes.items(), key=lambda kv: kv[1]["ms"])
     avg_ms = top["ms"] / top["n"]
     if top["kind"] == "conv" and top["flops"] / max(top["bytes"], 1) > tf_sustained * 1e12 / (hbm_peak * 1e9):
@@ -316,6 +327,8 @@ def run_train(args):
             f.write(f"# train step, per-kernel-class device time, eager replay with CUDA events, batch {B}; total {total_ms:.3f} ms; "
                     f"graph step {ms_step:.3f} ms\n")
             f.write(f"# launch DAG: {json.dumps(dag_info)}\n")
+            top_crit = sorted(crit.items(), key=lambda kv: -kv[1][1])[:40]
+            f.write("# critical chain by class (launches, ms): " + "; ".join(f"{k} {v[0]} {v[1]:.3f}" for k, v in top_crit) + "\n")
             f.write("class,launches,total_ms,avg_ms,share,TFLOP/s,GB/s\n")
             for name, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
                 a = c["ms"] / c["n"]

@@ -45,15 +45,47 @@ class FusedRMSprop(object):
         self.engine.rmsprop(g['lr'], g['alpha'], g['eps'])
 
     def state_dict(self):
+        """torch.optim.RMSprop's own state_dict layout (what the reference saves under 'optimizer', trainer.py:172,
+        and feeds back through optimizer.load_state_dict on resume, trainer.py:71): per-parameter 'step' and
+        'square_avg' indexed by position in model.parameters(), so checkpoints travel both ways."""
         st = self.engine.store
-        return {'param_groups': self.param_groups,
-                'square_avg': {k: st.view(st.V, k).detach().clone().contiguous() for k in st.slots}}
+        names = list(st.slots)
+        g = self.param_groups[0]
+        group = {'lr': g['lr'], 'momentum': 0, 'alpha': g['alpha'], 'eps': g['eps'], 'centered': False, 'weight_decay': 0,
+                 'capturable': False, 'foreach': None, 'maximize': False, 'differentiable': False,
+                 'params': list(range(len(names)))}
+        state = {}
+        if self.engine.steps > 0:
+            for i, k in enumerate(names):
+                state[i] = {'step': torch.tensor(float(self.engine.steps)),
+                            'square_avg': st.view(st.V, k).detach().clone().contiguous()}
+        return {'state': state, 'param_groups': [group]}
 
     def load_state_dict(self, sd):
-        self.param_groups = sd['param_groups']
         st = self.engine.store
-        for k, v in sd['square_avg'].items():
-            st.view(st.V, k).copy_(v)
+        names = list(st.slots)
+        if 'square_avg' in sd:                       # this build's earlier layout: {name: tensor}
+            for k, v in sd['square_avg'].items():
+                st.view(st.V, k).copy_(v)
+            self.param_groups[0].update({k: v for k, v in sd['param_groups'][0].items() if k in ('lr', 'alpha', 'eps')})
+            return
+        group = sd['param_groups'][0]
+        if group.get('momentum', 0) != 0 or group.get('centered', False) or group.get('weight_decay', 0) != 0:
+            raise ValueError("FusedRMSprop implements the reference's configuration only: momentum=0, centered=False, "
+                             "weight_decay=0 (trainer.py:39-41)")
+        self.param_groups[0].update(lr=group['lr'], alpha=group.get('alpha', RMSPROP_ALPHA), eps=group.get('eps', RMSPROP_EPS))
+        order = group['params']
+        if len(order) != len(names):
+            raise ValueError(f"optimizer state has {len(order)} parameters, the model has {len(names)}")
+        steps = 0
+        for pos, idx in enumerate(order):
+            ent = sd['state'].get(idx)
+            if ent is None:
+                st.view(st.V, names[pos]).zero_()
+                continue
+            st.view(st.V, names[pos]).copy_(ent['square_avg'])
+            steps = max(steps, int(float(ent.get('step', 0))))
+        self.engine.steps = steps
 
 
 class Trainer(object):
@@ -96,7 +128,7 @@ class Trainer(object):
         self.best_acc = checkpoint['best_acc']
         sd = {(k[7:] if k.startswith('module.') else k): v for k, v in checkpoint['state_dict'].items()}
         self.model.load_state_dict(sd)
-        if 'square_avg' in checkpoint.get('optimizer', {}):
+        if checkpoint.get('optimizer'):
             self.optimizer.load_state_dict(checkpoint['optimizer'])
 
     def state(self, epoch):
