@@ -68,6 +68,8 @@ _SIGNATURES = {
                         C.c_int),
     "hg_bn_bwd_reduce": ([_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp], C.c_int),
     "hg_bn_bwd_apply": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_normalize_u8_nhwc": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_preprocess_frames_u8": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_dwconv3x3_nhwc": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_dwconv3x3_wgrad": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_maxpool2x2_bwd_nhwc": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),

@@ -174,6 +174,48 @@ def stem_conv(packed: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, ou
     return out
 
 
+def normalize_u8(images_u8: torch.Tensor, mean, std, *, out: Optional[torch.Tensor] = None,
+                 packed: Optional[torch.Tensor] = None, flip_w: bool = False) -> torch.Tensor:
+    """ToTensor + Normalize on the device (hg_normalize_u8_nhwc): uint8 [n,h,w,3] -> fp32 NCHW [n,3,h,w], bit-identical
+    to torch's float32 arithmetic; `packed` additionally receives the stem's NHWC4 bf16 staging image."""
+    _require_cuda(images_u8, out, packed)
+    if images_u8.dtype != torch.uint8 or images_u8.dim() != 4 or images_u8.shape[3] != 3 or not images_u8.is_contiguous():
+        raise HgError("normalize_u8: expects a contiguous uint8 [n,h,w,3] tensor")
+    n, h, w, _ = images_u8.shape
+    if out is None and packed is None:
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=images_u8.device)
+    if out is not None and (tuple(out.shape) != (n, 3, h, w) or out.dtype != torch.float32 or not out.is_contiguous()):
+        raise HgError("normalize_u8: out must be a contiguous fp32 [n,3,h,w] tensor")
+    if packed is not None and (tuple(packed.shape) != (n, h, w + 8, 4) or packed.dtype != torch.bfloat16):
+        raise HgError("normalize_u8: packed must be a bf16 [n,h,w+8,4] buffer (stem_packed_buffer)")
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    sd = (C.c_float * 3)(*[float(v) for v in std])
+    lib.check(lib.hg_normalize_u8_nhwc(_ptr(images_u8), m, sd, _ptr(out), _ptr(packed), n, h, w, int(flip_w), _stream()),
+              "hg_normalize_u8_nhwc")
+    return out if out is not None else packed
+
+
+def preprocess_frames_u8(frames_u8: torch.Tensor, mean, std, size, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched Estimator.preprocess_bbox (hg_preprocess_frames_u8): uint8 [n,fh,fw,3] frames -> /255, float64 mean/std
+    (None: no normalisation), cv2-style bilinear resize to size=(width, height), fp32 NCHW [n,3,height,width]."""
+    _require_cuda(frames_u8, out)
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3 or not frames_u8.is_contiguous():
+        raise HgError("preprocess_frames_u8: expects a contiguous uint8 [n,fh,fw,3] tensor")
+    n, fh, fw, _ = frames_u8.shape
+    w, h = int(size[0]), int(size[1])
+    if out is None:
+        out = torch.empty((n, 3, h, w), dtype=torch.float32, device=frames_u8.device)
+    elif tuple(out.shape) != (n, 3, h, w) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise HgError("preprocess_frames_u8: out must be a contiguous fp32 [n,3,h,w] tensor")
+    if (mean is None) != (std is None):
+        raise HgError("preprocess_frames_u8: mean and std go together")
+    m = (C.c_double * 3)(*[float(v) for v in mean]) if mean is not None else None
+    sd = (C.c_double * 3)(*[float(v) for v in std]) if std is not None else None
+    lib.check(lib.hg_preprocess_frames_u8(_ptr(frames_u8), m, sd, _ptr(out), n, fh, fw, h, w, _stream()),
+              "hg_preprocess_frames_u8")
+    return out
+
+
 def maxpool2x2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _require_cuda(x, out)
     n, h, w, c = x.shape

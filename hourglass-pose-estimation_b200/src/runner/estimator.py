@@ -4,7 +4,8 @@
 frame*4/200/heat-map size): as SURVEY.md A14 records, that choice treats heat-map coordinates as if they were in
 frame space, so every keypoint lands within a few pixels of the frame centre -- the parity target is the
 FUNCTION get_final_preds_v1 with explicit arguments, and this caller is kept only so the entry point exists.
-`np.int` (removed in numpy 1.24, estimator.py:73,82) is spelled `int`.  cv2 is only needed by preprocess_bbox."""
+`np.int` (removed in numpy 1.24, estimator.py:73,82) is spelled `int`.  preprocess_bbox runs on the device
+(uint8 frame in, one kernel for /255, mean/std and cv2's bilinear resize): cv2 is not needed at all."""
 import os
 import time
 from collections import OrderedDict
@@ -43,21 +44,35 @@ class Estimator:
         self.model.to(self.device)
         self.model.eval()
 
+    # estimator.py:41-48 (frame channel order, float64)
+    MEAN_STD = (('coco', [0.4003, 0.4314, 0.4534], [0.2466, 0.2467, 0.2562]),
+                ('mpii', [0.4327, 0.4440, 0.4404], [0.2468, 0.2410, 0.2458]),
+                ('merl', [0.4785, 0.5036, 0.5078], [0.2306, 0.2289, 0.2326]),
+                ('se7en11', [0.5109, 0.5502, 0.5285], [0.2772, 0.2416, 0.2478]))
+
+    def _mean_std(self):
+        for key, mean, std in self.MEAN_STD:          # the reference's if/elif chain: first match wins
+            if key in self.dataset:
+                return mean, std
+        return None, None
+
+    def preprocess_frames(self, frames):
+        """Batch form of preprocess_bbox on the device: uint8 [n, fh, fw, 3] (numpy or tensor) -> fp32 [n, 3, in_res,
+        in_res] CUDA tensor.  Only the uint8 frames cross PCIe (a twelfth of the reference's float64 work, a quarter
+        of its float32 tensor); /255, mean/std and the bilinear resize run in one kernel (hg_preprocess_frames_u8)."""
+        from hgb200 import ops
+        t = torch.as_tensor(np.ascontiguousarray(frames)) if not torch.is_tensor(frames) else frames.contiguous()
+        if t.dtype != torch.uint8:
+            raise TypeError(f"preprocess_frames expects uint8 frames (cv2.imread's type), got {t.dtype}")
+        mean, std = self._mean_std()
+        return ops.preprocess_frames_u8(t.to(self.device, non_blocking=True), mean, std, self.input_size)
+
     def preprocess_bbox(self, bbox):
-        import cv2
-        in_frame = bbox / 255.0
-        if 'coco' in self.dataset:
-            in_frame = (in_frame - np.array([[[0.4003, 0.4314, 0.4534]]])) / np.array([[[0.2466, 0.2467, 0.2562]]])
-        elif 'mpii' in self.dataset:
-            in_frame = (in_frame - np.array([[[0.4327, 0.4440, 0.4404]]])) / np.array([[[0.2468, 0.2410, 0.2458]]])
-        elif 'merl' in self.dataset:
-            in_frame = (in_frame - np.array([[[0.4785, 0.5036, 0.5078]]])) / np.array([[[0.2306, 0.2289, 0.2326]]])
-        elif 'se7en11' in self.dataset:
-            in_frame = (in_frame - np.array([[[0.5109, 0.5502, 0.5285]]])) / np.array([[[0.2772, 0.2416, 0.2478]]])
-        in_frame = cv2.resize(in_frame, self.input_size)
-        in_frame = in_frame.transpose((2, 0, 1))
-        in_frame = in_frame.reshape((1, 3, self.input_size[0], self.input_size[1]))
-        return torch.from_numpy(in_frame).float().to(self.device)
+        """estimator.py:39-54: one HWC frame -> fp32 [1, 3, in_res, in_res] on the device."""
+        bbox = np.asarray(bbox)
+        if bbox.dtype != np.uint8:
+            raise TypeError(f"preprocess_bbox expects a uint8 HWC frame (cv2.imread's type), got {bbox.dtype}")
+        return self.preprocess_frames(bbox[None])
 
     def post_process_heatmap_v1(self, heatmaps, output_size):
         heatmaps = heatmaps.cpu().numpy()[0]

@@ -88,6 +88,21 @@ int64_t hg_halo_padded_elems(int32_t n, int32_t h, int32_t w, int32_t c);
 int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, const float* bias, void* out, unsigned int* err_word,
                          int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t relu, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Input preprocessing (the step before the path).  mean3 / std3 are HOST arrays.
+ * ------------------------------------------------------------------------------------------- */
+/* transforms.ToTensor() + Normalize(mean, std) (src/datasets/common.py:57-64) on uint8 HWC crops [n][h][w][3]:
+ * float32 (x/255 - mean[c]) / std[c] with IEEE division (bit-identical to torch).  Writes fp32 NCHW
+ * [n][3][h][w] (out_nchw, may be NULL) and/or the stem's packed NHWC4 bf16 staging image [n][h][w+8][4]
+ * (packed, may be NULL; interior only, flip_w mirrors) -- hg_stem_pack's layout. */
+int hg_normalize_u8_nhwc(const void* in_u8, const float* mean3, const float* std3, float* out_nchw, void* packed,
+                         int32_t n, int32_t h, int32_t w, int32_t flip_w, void* stream);
+/* Estimator.preprocess_bbox (src/runner/estimator.py:39-54) for n equally sized uint8 HWC frames [n][fh][fw][3]:
+ * x/255, (x - mean[c]) / std[c] in float64 (skipped when mean3 == std3 == NULL: the reference's datasets without
+ * a branch), cv2.resize(INTER_LINEAR) to (w, h) in float64, cast to float32 NCHW [n][3][h][w]. */
+int hg_preprocess_frames_u8(const void* frames_u8, const double* mean3, const double* std3, float* out_nchw, int32_t n,
+                            int32_t fh, int32_t fw, int32_t h, int32_t w, void* stream);
+
 /* Stem: conv 7x7 stride 2 pad 3 (3 -> cout) + folded BN + ReLU (src/models/hourglass.py:71-73).
  * Step 1 gathers NCHW fp32 pixels into K-major bf16 rows [n*oh*ow][192] (k = (ky*7+kx)*3 + c,
  * zero padded 147 -> 192); flip_w != 0 reads the image mirrored left-right (flip test).

@@ -115,3 +115,23 @@ def test_flip_average_definition():
     # a model that is exactly flip-equivariant returns hm itself after flip-back
     hm_f = hm[:, perm][:, :, :, ::-1]
     np.testing.assert_array_equal(D.flip_average(hm, hm_f, D.MPII_FLIP_PAIRS), hm)
+
+
+def test_preprocess_oracle_matches_reference():
+    """oracle/preprocess_oracle.py against Estimator.preprocess_bbox and ToTensor+Normalize run live
+    (oracle/make_golden_preprocess.py).  ToTensor+Normalize is float32 arithmetic: bit-exact.  preprocess_bbox goes
+    through cv2.resize in float64 whose summation order OpenCV does not document: the restatement agrees to 1e-15 in
+    float64, i.e. after the reference's own cast to float32 it is identical up to a rare last-bit flip (<= 1 ulp)."""
+    from oracle import preprocess_oracle as P
+    z = np.load(os.path.join(GOLDEN, "preprocess.npz"))
+    for i in range(int(z["n_crops"])):
+        got = P.normalize_u8(z[f"crop{i}"], z["crop_mean"], z["crop_std"])
+        assert got.dtype == np.float32 and np.array_equal(got, z[f"crop_out{i}"])
+    for i in range(int(z["n_frames"])):
+        dataset, res = str(z[f"frame_cfg{i}"][0]), int(z[f"frame_cfg{i}"][1])
+        got = P.preprocess_bbox(z[f"frame{i}"], dataset, (res, res))
+        ref = z[f"frame_out{i}"]
+        assert got.shape == ref.shape == (1, 3, res, res) and got.dtype == np.float32
+        ulp = np.spacing(np.abs(ref).astype(np.float32))
+        assert np.all(np.abs(got - ref) <= ulp)
+        assert np.mean(got != ref) < 1e-3
