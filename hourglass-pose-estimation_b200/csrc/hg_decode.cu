@@ -196,6 +196,130 @@ __global__ void __launch_bounds__(kDecThreads) pck_dists_kernel(const float* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// DARK-style decode: get_final_preds_v2 (src/utils/inference.py:9-45,70-87), one CTA per (image, joint) map.
+//   1. flat arg-max (first maximum) and the map's maximum;
+//   2. 11x11 separable Gaussian blur (sigma 2, OpenCV's getGaussianKernel(11, 0) weights) of the zero-padded map in
+//      float64 -- rows (taps left to right) then columns (centre, then symmetric pairs), no fused multiply-add --
+//      each value stored as float32, as the reference's float32 array does (inference.py:43);
+//   3. the blurred map rescaled so that its maximum is the original maximum (float32), log(max(., 1e-10));
+//   4. second-order Taylor step from the 13-point stencil around the arg-max for the first `refine_joints` joints
+//      (the reference's loop runs over coords.shape[1] == 2, i.e. joints 0 and 1 only), float32, 2x2 inverse by
+//      LU with partial pivoting as LAPACK's gesv does;
+//   5. the inverse affine of get_final_preds_v1, float64.
+// ---------------------------------------------------------------------------------------------
+__constant__ double c_gauss11[11] = {
+    0x1.20c2564ee6772p-7, 0x1.bcb86a082c301p-6, 0x1.0ab50979aaf94p-4, 0x1.f2464c62edaf4p-4, 0x1.6a7e1d504a91dp-3,
+    0x1.9ac20a36ea596p-3, 0x1.6a7e1d504a91dp-3, 0x1.f2464c62edaf4p-4, 0x1.0ab50979aaf94p-4, 0x1.bcb86a082c301p-6,
+    0x1.20c2564ee6772p-7};
+
+__global__ void __launch_bounds__(kDecThreads) decode_dark_kernel(const float* __restrict__ hm, const double* __restrict__ center,
+                                                                   const double* __restrict__ scale, double* __restrict__ out,
+                                                                   int nj, int h, int w, int out_w, int out_h,
+                                                                   int refine_joints) {
+    extern __shared__ __align__(16) unsigned char dark_smem[];
+    double* rows = reinterpret_cast<double*>(dark_smem);                 // [h][w] row-pass result
+    float* blur = reinterpret_cast<float*>(rows + h * w);                // [h][w] blurred map, float32
+    __shared__ float s_red[kDecThreads / 32];
+    __shared__ ArgMax s_arg;
+    const int m = blockIdx.x;
+    const int hw = h * w;
+    const float* map = hm + static_cast<long long>(m) * hw;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int joint = m % nj;
+    const bool refine = joint < refine_joints;
+    if (warp == 0) {
+        const ArgMax a = warp_argmax(map, hw, lane);
+        if (lane == 0) s_arg = a;
+    }
+    float bmax = -INFINITY;
+    if (refine) {
+        for (int i = threadIdx.x; i < hw; i += kDecThreads) {
+            const int y = i / w, x = i - y * w;
+            const float* r = map + y * w;
+            double s = __dmul_rn(c_gauss11[0], (x - 5 >= 0) ? static_cast<double>(__ldg(r + x - 5)) : 0.0);
+#pragma unroll
+            for (int t = 1; t < 11; ++t) {
+                const int xx = x + t - 5;
+                const double v = (xx >= 0 && xx < w) ? static_cast<double>(__ldg(r + xx)) : 0.0;
+                s = __dadd_rn(s, __dmul_rn(c_gauss11[t], v));
+            }
+            rows[i] = s;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < hw; i += kDecThreads) {
+            const int y = i / w, x = i - y * w;
+            double s = __dmul_rn(c_gauss11[5], rows[i]);
+#pragma unroll
+            for (int t = 1; t <= 5; ++t) {
+                const double lo = (y - t >= 0) ? rows[(y - t) * w + x] : 0.0;
+                const double hi = (y + t < h) ? rows[(y + t) * w + x] : 0.0;
+                s = __dadd_rn(s, __dmul_rn(c_gauss11[5 + t], __dadd_rn(hi, lo)));
+            }
+            const float f = static_cast<float>(s);
+            blur[i] = f;
+            bmax = fmaxf(bmax, f);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, off));
+        if (lane == 0) s_red[warp] = bmax;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const ArgMax a = s_arg;
+    float x, y;
+    quirk_coords(a.i, w, x, y);
+    if (!(a.v > 0.f)) { x = 0.f; y = 0.f; }
+    if (refine) {
+        float mb = s_red[0];
+        for (int i = 1; i < kDecThreads / 32; ++i) mb = fmaxf(mb, s_red[i]);
+        const float ratio = __fdiv_rn(a.v, mb);                          // origin_max / max(blurred), float32
+        const int px = static_cast<int>(x), py = static_cast<int>(y);    // int(): truncation
+        if (1 < px && px < w - 2 && 1 < py && py < h - 2) {
+            auto L = [&](int yy, int xx) -> float {
+                const float v = fmaxf(__fmul_rn(blur[yy * w + xx], ratio), 1e-10f);
+                return static_cast<float>(log(static_cast<double>(v)));
+            };
+            const float c0 = L(py, px);
+            const float dx = __fmul_rn(0.5f, __fsub_rn(L(py, px + 1), L(py, px - 1)));
+            const float dy = __fmul_rn(0.5f, __fsub_rn(L(py + 1, px), L(py - 1, px)));
+            const float dxx = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(L(py, px + 2), __fmul_rn(2.f, c0)), L(py, px - 2)));
+            const float dxy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(__fsub_rn(L(py + 1, px + 1), L(py - 1, px + 1)),
+                                                                   L(py + 1, px - 1)), L(py - 1, px - 1)));
+            const float dyy = __fmul_rn(0.25f, __fadd_rn(__fsub_rn(L(py + 2, px), __fmul_rn(2.f, c0)), L(py - 2, px)));
+            if (__fsub_rn(__fmul_rn(dxx, dyy), __fmul_rn(dxy, dxy)) != 0.f) {
+                // inverse of [[dxx, dxy], [dxy, dyy]]: LU with partial pivoting, then the two unit right-hand sides
+                float a00 = dxx, a01 = dxy, a10 = dxy, a11 = dyy;
+                const bool swap = fabsf(a10) > fabsf(a00);
+                if (swap) { float t0 = a00; a00 = a10; a10 = t0; t0 = a01; a01 = a11; a11 = t0; }
+                const float l = __fmul_rn(a10, __fdiv_rn(1.f, a00));
+                const float u11 = __fsub_rn(a11, __fmul_rn(l, a01));
+                // columns of the inverse: solve for P*e0 and P*e1
+                float inv[2][2];
+#pragma unroll
+                for (int col = 0; col < 2; ++col) {
+                    float b0 = col == 0 ? 1.f : 0.f, b1 = col == 0 ? 0.f : 1.f;
+                    if (swap) { const float t0 = b0; b0 = b1; b1 = t0; }
+                    const float y1 = __fsub_rn(b1, __fmul_rn(l, b0));
+                    const float x1 = __fdiv_rn(y1, u11);
+                    const float x0 = __fdiv_rn(__fsub_rn(b0, __fmul_rn(a01, x1)), a00);
+                    inv[0][col] = x0;
+                    inv[1][col] = x1;
+                }
+                const float ox = -__fadd_rn(__fmul_rn(inv[0][0], dx), __fmul_rn(inv[0][1], dy));
+                const float oy = -__fadd_rn(__fmul_rn(inv[1][0], dx), __fmul_rn(inv[1][1], dy));
+                x = __fadd_rn(x, ox);
+                y = __fadd_rn(y, oy);
+            }
+        }
+    }
+    const int b = m / nj;
+    const Affine A = inverse_affine(center[2 * b], center[2 * b + 1], scale[2 * b], out_w, out_h);
+    const double xd = x, yd = y;
+    out[2 * m] = A.m[0] * xd + A.m[1] * yd + A.m[2];
+    out[2 * m + 1] = A.m[3] * xd + A.m[4] * yd + A.m[5];
+}
+
 static int dec_grid(int maps) {
     const int blocks = (maps + kDecThreads / 32 - 1) / (kDecThreads / 32);
     const int cap = num_sms() * 8;
@@ -271,6 +395,23 @@ extern "C" int hg_pck_dists(const float* out_hm, const float* tgt_hm, float* dis
     }
     pck_dists_kernel<<<dec_grid(b * j), kDecThreads, 0, static_cast<cudaStream_t>(stream)>>>(out_hm, tgt_hm, dists, b, j, h,
                                                                                               w);
+    HG_CUDA_OK(cudaGetLastError());
+    return HG_OK;
+}
+
+extern "C" int hg_decode_final_preds_v2(const float* hm, const double* center, const double* scale, double* out, int32_t b,
+                                        int32_t j, int32_t h, int32_t w, int32_t out_w, int32_t out_h, int32_t refine_joints,
+                                        void* stream) {
+    int rc = check_maps("hg_decode_final_preds_v2", b, j, h, w);
+    if (rc) return rc;
+    const size_t smem = static_cast<size_t>(h) * w * (sizeof(double) + sizeof(float));
+    if (!hm || !center || !scale || !out || out_w <= 0 || out_h <= 0 || refine_joints < 0 || smem > 200 * 1024) {
+        set_last_error("hg_decode_final_preds_v2: null pointer, bad output size, or map larger than 128x128");
+        return HG_ERR_INVALID;
+    }
+    HG_CUDA_OK(cudaFuncSetAttribute(decode_dark_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    decode_dark_kernel<<<b * j, kDecThreads, smem, static_cast<cudaStream_t>(stream)>>>(hm, center, scale, out, j, h, w, out_w,
+                                                                                         out_h, refine_joints);
     HG_CUDA_OK(cudaGetLastError());
     return HG_OK;
 }

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "hg_nhwc_bf16_to_nchw_f32": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_decode_argmax": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_decode_final_preds": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_decode_final_preds_v2": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_flip_average": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_pck_dists": ([_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_joint_centers": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),

@@ -295,6 +295,19 @@ def decode_final_preds(hm: torch.Tensor, center, scale, output_size) -> torch.Te
     return out
 
 
+def decode_final_preds_v2(hm: torch.Tensor, center, scale, output_size, refine_joints: int = 2) -> torch.Tensor:
+    """Batched get_final_preds_v2 (DARK-style; hg_decode_final_preds_v2): center/scale [b,2] -> fp64 [b,j,2] on device.
+    refine_joints=2 is the reference's behaviour (its loop refines joints 0 and 1 only); pass j to refine all."""
+    hm = _hm(hm)
+    b, j, h, w = hm.shape
+    c = torch.as_tensor(np.asarray(center, dtype=np.float64).reshape(b, 2)).to(hm.device)
+    s = torch.as_tensor(np.asarray(scale, dtype=np.float64).reshape(b, 2)).to(hm.device)
+    out = torch.empty((b, j, 2), dtype=torch.float64, device=hm.device)
+    lib.check(lib.hg_decode_final_preds_v2(_ptr(hm), _ptr(c), _ptr(s), _ptr(out), b, j, h, w, int(output_size[0]),
+                                           int(output_size[1]), int(refine_joints), _stream()), "hg_decode_final_preds_v2")
+    return out
+
+
 def decode_final_preds_into(hm, center, scale, out, output_size):
     """Pointer-stable form for static plans: every argument is a preallocated device tensor."""
     _require_cuda(hm, center, scale, out)

@@ -147,6 +147,14 @@ int hg_decode_argmax(const float* hm, float* preds, float* maxval, int32_t* argi
  * affine.  center/scale: fp64 [b][2]; out: fp64 [b][j][2].  out_w/out_h = `output_size`. */
 int hg_decode_final_preds(const float* hm, const double* center, const double* scale, double* out, int32_t b,
                           int32_t j, int32_t h, int32_t w, int32_t out_w, int32_t out_h, void* stream);
+
+/* get_final_preds_v2 (src/utils/inference.py:70-87, DARK-style) for EVERY image of the batch: arg-max, 11x11
+ * Gaussian blur (sigma 2) of the zero-padded map in float64 rescaled to the original peak, log(max(., 1e-10)),
+ * second-order Taylor step for joints [0, refine_joints) -- the reference's loop covers joints 0 and 1 only
+ * (`range(coords.shape[1])`, :79): pass 2 for parity, j for every joint -- then the same inverse affine.
+ * Maps up to 128x128. */
+int hg_decode_final_preds_v2(const float* hm, const double* center, const double* scale, double* out, int32_t b, int32_t j,
+                             int32_t h, int32_t w, int32_t out_w, int32_t out_h, int32_t refine_joints, void* stream);
 /* flip-test merge (defined from the reference's flip_pairs):
  * out[b][k] = 0.5*(hm[b][k] + mirror_w(hm_flip[b][perm[k]])) ; perm: int32 [j] on the device. */
 int hg_flip_average(const float* hm, const float* hm_flip, const int32_t* perm, float* out, int32_t b, int32_t j,

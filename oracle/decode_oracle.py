@@ -168,3 +168,80 @@ def flip_average(hm: np.ndarray, hm_flipped_input: np.ndarray, flip_pairs) -> np
     perm = flip_perm(hm.shape[1], flip_pairs)
     back = hm_flipped_input[:, :, :, ::-1][:, perm]
     return (np.float32(0.5) * (hm.astype(np.float32) + back.astype(np.float32))).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# DARK-style decode: get_final_preds_v2, src/utils/inference.py:9-45,70-87  
+# ---------------------------------------------------------------------------------------------
+# cv2.getGaussianKernel(11, 0) in float64 (sigma = 0.3*((11-1)*0.5 - 1) + 0.8 = 2.0), OpenCV 4.13.0 -- the arithmetic
+# lives in OpenCV (unpinned by the reference); the eleven weights are recorded here so that the restatement does
+# not depend on cv2.
+GAUSS11 = np.array([float.fromhex(v) for v in (
+    '0x1.20c2564ee6772p-7', '0x1.bcb86a082c301p-6', '0x1.0ab50979aaf94p-4', '0x1.f2464c62edaf4p-4',
+    '0x1.6a7e1d504a91dp-3', '0x1.9ac20a36ea596p-3', '0x1.6a7e1d504a91dp-3', '0x1.f2464c62edaf4p-4',
+    '0x1.0ab50979aaf94p-4', '0x1.bcb86a082c301p-6', '0x1.20c2564ee6772p-7')])
+
+
+def blur11_zero_padded(hm: np.ndarray) -> np.ndarray:
+    """inference.py:37-43 for one map: the map is embedded in a zero frame 5 px wide, blurred with the separable
+    11-tap Gaussian in float64 and cropped back, so the frame's own border mode never reaches the crop: a
+    zero-padded convolution.  Rows first (taps left to right), then columns (centre, then symmetric pairs); OpenCV's
+    exact summation order is not documented -- agreement with cv2.GaussianBlur is ~1e-16, which the reference's own
+    store into a float32 array erases except for a rare last-bit flip."""
+    h, w = hm.shape
+    k = GAUSS11
+    a = np.zeros((h, w + 10), dtype=np.float64)
+    a[:, 5:-5] = hm
+    rows = np.zeros((h + 10, w), dtype=np.float64)
+    acc = k[0] * a[:, 0:w]
+    for t in range(1, 11):
+        acc = acc + k[t] * a[:, t:t + w]
+    rows[5:-5] = acc
+    out = k[5] * rows[5:5 + h]
+    for t in range(1, 6):
+        out = out + k[5 + t] * (rows[5 + t:5 + t + h] + rows[5 - t:5 - t + h])
+    return out
+
+
+def gaussian_blur(hm: np.ndarray) -> np.ndarray:
+    """inference.py:32-45 on float32 [B,J,h,w]: blur, then rescale so the maximum is the original maximum; every
+    store goes through the float32 array (as in the reference, where hms is the float32 view of the tensor)."""
+    hm = hm.astype(np.float32).copy()
+    B, J = hm.shape[:2]
+    for i in range(B):
+        for j in range(J):
+            origin_max = np.max(hm[i, j])
+            hm[i, j] = blur11_zero_padded(hm[i, j].astype(np.float64))
+            hm[i, j] *= origin_max / np.max(hm[i, j])
+    return hm
+
+
+def taylor(hm: np.ndarray, coord: np.ndarray) -> np.ndarray:
+    """inference.py:9-29; hm float32 [h,w] (log heat map), coord float32 [2] (quirk coordinates)."""
+    H, W = hm.shape
+    px, py = int(coord[0]), int(coord[1])
+    coord = coord.astype(np.float32).copy()
+    if 1 < px < W - 2 and 1 < py < H - 2:
+        dx = 0.5 * (hm[py][px + 1] - hm[py][px - 1])
+        dy = 0.5 * (hm[py + 1][px] - hm[py - 1][px])
+        dxx = 0.25 * (hm[py][px + 2] - 2 * hm[py][px] + hm[py][px - 2])
+        dxy = 0.25 * (hm[py + 1][px + 1] - hm[py - 1][px + 1] - hm[py + 1][px - 1] + hm[py - 1][px - 1])
+        dyy = 0.25 * (hm[py + 2][px] - 2 * hm[py][px] + hm[py - 2][px])
+        derivative = np.array([[dx], [dy]])
+        hessian = np.array([[dxx, dxy], [dxy, dyy]])
+        if dxx * dyy - dxy ** 2 != 0:
+            offset = -np.dot(np.linalg.inv(hessian), derivative)
+            coord = (coord + np.squeeze(np.array(offset.T), axis=0).astype(np.float32)).astype(np.float32)
+    return coord
+
+
+def get_final_preds_v2(hms: np.ndarray, center, scale, output_size, refine_joints: int = 2) -> np.ndarray:
+    """inference.py:70-87 -- batch element 0 only.  The reference's loop is `for p in range(coords.shape[1])` with
+    coords of shape [J, 2], so only joints 0 and 1 get the Taylor step (refine_joints=2 reproduces that; pass J for
+    what the loop presumably meant)."""
+    coords = get_preds(hms)[0]
+    h = gaussian_blur(hms[:1])
+    h = np.log(np.maximum(h, np.float32(1e-10)))
+    for p in range(min(refine_joints, coords.shape[0])):
+        coords[p] = taylor(h[0][p], coords[p])
+    return transform_preds(coords, center, scale, output_size)

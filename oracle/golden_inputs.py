@@ -129,3 +129,36 @@ def loss_cases(seed=23):
         noise = [(0.3 * rng.randn(B, J, hsz[1], hsz[0])).astype(np.float32) for _ in range(S)]
         cases.append(dict(joints=joints, vis=vis, isz=isz, hsz=hsz, S=S, noise=noise))
     return cases
+
+
+def dark_cases(seed=29):
+    """Inputs for get_final_preds_v2 (batch element 0 is what the reference decodes): Gaussian blobs at sub-pixel
+    centres (well-conditioned Hessians), blobs on the border (the guard skips the Taylor step), a non-square map,
+    and one plain random map (ill-conditioned: the Taylor step can be large)."""
+    rng = np.random.RandomState(seed)
+    cases = []
+
+    def blobs(J, H, W, lo, hi, noise):
+        ys, xs = np.mgrid[0:H, 0:W].astype(np.float64)
+        hm = np.zeros((1, J, H, W), np.float32)
+        for j in range(J):
+            cx, cy = rng.uniform(lo, W - lo), rng.uniform(lo, H - lo)
+            s = rng.uniform(1.0, 2.5)
+            hm[0, j] = (hi * np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / (2 * s * s)) + noise * rng.rand(H, W)).astype(np.float32)
+        return hm
+
+    for _ in range(6):
+        cases.append(dict(hm=blobs(16, 64, 64, 6.0, rng.uniform(0.3, 1.0), 1e-3)))
+    cases.append(dict(hm=blobs(17, 64, 48, 6.0, 0.9, 1e-3)))
+    cases.append(dict(hm=blobs(16, 64, 64, -1.0, 0.8, 1e-3)))        # some centres on / beyond the border
+    cases.append(dict(hm=blobs(4, 16, 16, 3.0, 0.7, 0.0)))
+    z = blobs(16, 64, 64, 6.0, 0.9, 0.0)
+    z[0, 1] = 0.0                                                      # empty map: maxval 0 -> coords (0,0), log(1e-10)
+    cases.append(dict(hm=z))
+    cases.append(dict(hm=rng.rand(1, 16, 64, 64).astype(np.float32)))
+    for c in cases:
+        H, W = c["hm"].shape[2:]
+        c["center"] = np.array([rng.uniform(50, 200), rng.uniform(50, 200)])
+        c["scale"] = np.array([rng.uniform(0.5, 2.5), rng.uniform(0.5, 2.5)])
+        c["output_size"] = (W, H)
+    return cases
