@@ -260,6 +260,23 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Column sums across a warp: on entry lane r holds v[0..31] = the 32 column values of row r; the return value on
+// lane c is sum over the 32 lanes of v[c].  A butterfly that halves the live values at every step: 31 shuffles
+// (instead of 32 x 5 for one reduction per column).  v is destroyed.
+__device__ __forceinline__ float warp_column_sum(float (&v)[32], uint32_t lane) {
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const bool upper = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < step; ++i) {
+            const float send = upper ? v[i] : v[i + step];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, step);
+            v[i] = (upper ? v[i + step] : v[i]) + recv;
+        }
+    }
+    return v[0];
+}
+
 // 128-bit streaming global access (bandwidth-bound kernels)
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     uint4 r;

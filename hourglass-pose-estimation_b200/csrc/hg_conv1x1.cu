@@ -44,6 +44,8 @@ struct Params {
     const float* in_scale;
     const float* in_shift;
     unsigned int* err_word;
+    float* stats;           // optional fp32 [2*cout]: per-channel sum | sum of squares of the epilogue's fp32 results, ADDED
+    int m_total;            // valid rows (the last tile may be ragged)
     int num_tiles;
     int kb1, kb2;           // k-blocks from `in` / from `in2`
     int cin;
@@ -57,7 +59,9 @@ enum : uint32_t { kErrProducer = 0x1100, kErrMma = 0x1200, kErrRing = 0x1300, kE
 template <int BLOCK_N>
 __host__ __device__ constexpr int w_bytes(int num_kb) { return num_kb * BLOCK_N * kBlockK * 2; }
 
-template <int BLOCK_N, bool kPrologue>
+// kStats: the epilogue also adds the per-channel sum / sum of squares of its results into p.stats.  A separate
+// instantiation so that the plain kernel (inference, dgrad) keeps its register budget and schedule.
+template <int BLOCK_N, bool kPrologue, bool kStats>
 __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const __grid_constant__ Params p) {
     constexpr int kBStage = BLOCK_N * kBlockK * 2;
     constexpr int kSlabs = BLOCK_N / 64;
@@ -71,7 +75,8 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
     uint8_t* smem_ring = smem_a + p.a_stages * kSlabBytes;         // ring x 16 KiB
     uint8_t* smem_up = smem_ring + p.ring * kSlabBytes;            // ring x 4 KiB (only if has_up)
     float* s_bias = reinterpret_cast<float*>(smem_up + (p.has_up ? p.ring * kUpBytes : 0));
-    float* s_scale = s_bias + BLOCK_N;
+    float* s_stats = s_bias + BLOCK_N;                             // [2*BLOCK_N] column sums of this CTA's tiles
+    float* s_scale = s_stats + (kStats ? 2 * BLOCK_N : 0);
     float* s_shift = s_scale + (kPrologue ? kMaxK : 0);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_shift + (kPrologue ? kMaxK : 0));
     uint64_t* full_bar = bars;                                     // [kMaxAStages]
@@ -88,6 +93,8 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
     const int lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (kStats)
+        for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) s_stats[i] = 0.f;
     if (kPrologue) {
         for (int i = threadIdx.x; i < p.cin; i += blockDim.x) {
             s_scale[i] = p.in_scale[i];
@@ -316,6 +323,23 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                         }
                         sts128(stg + (((half * 4 + i) ^ (row & 7)) << 4), o);
                     }
+                    if (kStats) {
+                        // per-channel sum / sum of squares of what this tile produced (train-mode BatchNorm statistics
+                        // of the NEXT layer, fused here so that no separate pass re-reads the tensor)
+                        const bool row_ok = m0 + row < p.m_total;
+                        float sq[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float t = p.relu ? fmaxf(f[i], 0.f) : f[i];
+                            t = row_ok ? t : 0.f;
+                            f[i] = t;
+                            sq[i] = t * t;
+                        }
+                        const float cs = warp_column_sum(f, lane);
+                        const float cq = warp_column_sum(sq, lane);
+                        atomicAdd(&s_stats[col0 + lane], cs);
+                        atomicAdd(&s_stats[BLOCK_N + col0 + lane], cq);
+                    }
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1, 128);
@@ -340,6 +364,10 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                     ring_phase ^= 1u;
                 }
             }
+        }
+        if (kStats) {
+            named_bar_sync(1, 128);
+            for (int i = threadIdx.x - 128; i < 2 * BLOCK_N; i += 128) atomicAdd(p.stats + i, s_stats[i]);
         }
         if (leader) tma_store_wait<0>();
     } else if (kPrologue && warp_idx >= 8) {
@@ -433,9 +461,9 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t r
     return HG_OK;
 }
 
-template <int BLOCK_N, bool kPrologue>
-static int launch(const Params& kp, int smem_bytes, cudaStream_t stream) {
-    auto kern = conv1x1_kernel<BLOCK_N, kPrologue>;
+template <int BLOCK_N, bool kPrologue, bool kStats>
+static int launch_variant(const Params& kp, int smem_bytes, cudaStream_t stream) {
+    auto kern = conv1x1_kernel<BLOCK_N, kPrologue, kStats>;
     static std::mutex mu;
     static unsigned long long done_mask = 0;
     int dev = 0;
@@ -450,6 +478,12 @@ static int launch(const Params& kp, int smem_bytes, cudaStream_t stream) {
     const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
     HG_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(kPrologue ? 384 : 256), smem_bytes, stream, kp));
     return HG_OK;
+}
+
+template <int BLOCK_N, bool kPrologue>
+static int launch(const Params& kp, int smem_bytes, cudaStream_t stream) {
+    return kp.stats != nullptr ? launch_variant<BLOCK_N, kPrologue, true>(kp, smem_bytes, stream)
+                               : launch_variant<BLOCK_N, kPrologue, false>(kp, smem_bytes, stream);
 }
 
 }  // namespace c1
@@ -488,6 +522,8 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
     kp.in_scale = d->in_scale;
     kp.in_shift = d->in_shift;
     kp.err_word = d->err_word;
+    kp.stats = d->stats;
+    kp.m_total = static_cast<int>(m);
     kp.num_tiles = static_cast<int>((m + kTileM - 1) / kTileM);
     kp.kb1 = d->cin / 64;
     kp.kb2 = d->cin2 / 64;
@@ -499,7 +535,7 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
     // shared-memory budget -> pipeline depths
     const int num_kb = kp.kb1 + kp.kb2;
     const int wbytes = num_kb * d->cout * kBlockK * 2;
-    const int misc = d->cout * 4 + (prologue ? 2 * kMaxK * 4 : 0) + 512;     // bias, scale/shift, barriers
+    const int misc = (d->stats ? 3 : 1) * d->cout * 4 + (prologue ? 2 * kMaxK * 4 : 0) + 512;   // bias, column sums, scale/shift, barriers
     int avail = kSmemLimit - 1024 - wbytes - misc;
     const int ring_unit = kSlabBytes + (kp.has_up ? kUpBytes : 0);
     const int slabs = d->cout / 64;

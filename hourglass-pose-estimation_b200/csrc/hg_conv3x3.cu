@@ -38,6 +38,7 @@ struct Params {
     const float* bias;
     __nv_bfloat16* out;     // dense NHWC [n][h][w][cout]
     unsigned int* err_word;
+    float* stats;           // optional fp32 [2*cout]: per-channel sum | sum of squares of the fp32 results, ADDED
     int H, W, P, NB;
     int cin, cout, slabs;
     int num_tiles;
@@ -47,7 +48,9 @@ struct Params {
     int relu;
 };
 
-template <int BLOCK_N>
+// kStats: the epilogue also adds the per-channel sum / sum of squares of its results into p.stats (a separate
+// instantiation: the plain kernel keeps its register budget and schedule).
+template <int BLOCK_N, bool kStats>
 __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__ Params p) {
     constexpr int kBStage = BLOCK_N * kBlockK * 2;
     constexpr int kTmemCols = 4 * BLOCK_N;            // 2 accumulator stages x 2 sub-tiles
@@ -57,7 +60,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
     uint8_t* smem_a = smem;                                    // 2 regions
     uint8_t* smem_b = smem_a + 2 * p.region_bytes;             // b_stages x kBStage
     float* s_bias = reinterpret_cast<float*>(smem_b + p.b_stages * kBStage);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
+    float* s_stats = s_bias + BLOCK_N;                          // [2*BLOCK_N]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + (kStats ? 2 * BLOCK_N : 0));
     uint64_t* a_full = bars;                  // [2]
     uint64_t* a_empty = bars + 2;             // [2]
     uint64_t* b_full = bars + 4;              // [kMaxBStages]
@@ -69,6 +73,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (kStats)
+        for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) s_stats[i] = 0.f;
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&p.map_a);
         tma_prefetch_desc(&p.map_b);
@@ -213,25 +219,60 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                     }
-                    if (valid) {
+                    if (!kStats) {
+                        if (valid) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float f8[8];
+                            for (int i = 0; i < 4; ++i) {
+                                float f8[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                f8[j] = __uint_as_float(v[i * 8 + j]) + s_bias[c0 + i * 8 + j];
-                                if (p.relu) f8[j] = fmaxf(f8[j], 0.f);
+                                for (int j = 0; j < 8; ++j) {
+                                    f8[j] = __uint_as_float(v[i * 8 + j]) + s_bias[c0 + i * 8 + j];
+                                    if (p.relu) f8[j] = fmaxf(f8[j], 0.f);
+                                }
+                                uint4 w4;
+                                w4.x = pack_bf16x2(f8[0], f8[1]);
+                                w4.y = pack_bf16x2(f8[2], f8[3]);
+                                w4.z = pack_bf16x2(f8[4], f8[5]);
+                                w4.w = pack_bf16x2(f8[6], f8[7]);
+                                *reinterpret_cast<uint4*>(o + c0 + i * 8) = w4;
                             }
-                            uint4 w4;
-                            w4.x = pack_bf16x2(f8[0], f8[1]);
-                            w4.y = pack_bf16x2(f8[2], f8[3]);
-                            w4.z = pack_bf16x2(f8[4], f8[5]);
-                            w4.w = pack_bf16x2(f8[6], f8[7]);
-                            *reinterpret_cast<uint4*>(o + c0 + i * 8) = w4;
                         }
+                    } else {
+                        float fv[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            fv[i] = __uint_as_float(v[i]) + s_bias[c0 + i];
+                            if (p.relu) fv[i] = fmaxf(fv[i], 0.f);
+                        }
+                        if (valid) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                uint4 w4;
+                                w4.x = pack_bf16x2(fv[i * 8 + 0], fv[i * 8 + 1]);
+                                w4.y = pack_bf16x2(fv[i * 8 + 2], fv[i * 8 + 3]);
+                                w4.z = pack_bf16x2(fv[i * 8 + 4], fv[i * 8 + 5]);
+                                w4.w = pack_bf16x2(fv[i * 8 + 6], fv[i * 8 + 7]);
+                                *reinterpret_cast<uint4*>(o + c0 + i * 8) = w4;
+                            }
+                        }
+                        // train-mode BatchNorm statistics of the next layer, fused: column sums over the valid rows
+                        float sq[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            fv[i] = valid ? fv[i] : 0.f;
+                            sq[i] = fv[i] * fv[i];
+                        }
+                        const float cs = warp_column_sum(fv, lane);
+                        const float cq = warp_column_sum(sq, lane);
+                        atomicAdd(&s_stats[c0 + lane], cs);
+                        atomicAdd(&s_stats[BLOCK_N + c0 + lane], cq);
                     }
                 }
             }
+        }
+        if (kStats) {
+            named_bar_sync(1, 128);
+            for (int i = threadIdx.x - 128; i < 2 * BLOCK_N; i += 128) atomicAdd(p.stats + i, s_stats[i]);
         }
     }
 
@@ -278,9 +319,9 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t r
     return HG_OK;
 }
 
-template <int BLOCK_N>
-static int launch(const Params& kp, int smem_bytes, cudaStream_t stream) {
-    auto kern = conv3x3_kernel<BLOCK_N>;
+template <int BLOCK_N, bool kStats>
+static int launch_variant(const Params& kp, int smem_bytes, cudaStream_t stream) {
+    auto kern = conv3x3_kernel<BLOCK_N, kStats>;
     static std::mutex mu;
     static unsigned long long done_mask = 0;
     int dev = 0;
@@ -297,6 +338,12 @@ static int launch(const Params& kp, int smem_bytes, cudaStream_t stream) {
     return HG_OK;
 }
 
+template <int BLOCK_N>
+static int launch(const Params& kp, int smem_bytes, cudaStream_t stream) {
+    return kp.stats != nullptr ? launch_variant<BLOCK_N, true>(kp, smem_bytes, stream)
+                               : launch_variant<BLOCK_N, false>(kp, smem_bytes, stream);
+}
+
 }  // namespace c3
 }  // namespace hg
 
@@ -306,7 +353,7 @@ extern "C" int64_t hg_halo_padded_elems(int32_t n, int32_t h, int32_t w, int32_t
 }
 
 extern "C" int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, const float* bias, void* out,
-                                    unsigned int* err_word, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                                    unsigned int* err_word, float* stats, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout,
                                     int32_t relu, void* stream) {
     using namespace hg;
     using namespace hg::c3;
@@ -320,6 +367,7 @@ extern "C" int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, c
     kp.bias = bias;
     kp.out = static_cast<__nv_bfloat16*>(out);
     kp.err_word = err_word;
+    kp.stats = stats;
     kp.H = h;
     kp.W = w;
     kp.P = w + 1;
@@ -335,7 +383,7 @@ extern "C" int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, c
     kp.box_rows = ((region_rows + kp.num_boxes - 1) / kp.num_boxes + 7) / 8 * 8;
     kp.region_bytes = kp.num_boxes * kp.box_rows * 128;
     const int b_stage = cout * 128;
-    const int misc = cout * 4 + 512;
+    const int misc = (stats ? 3 : 1) * cout * 4 + 512;
     int b_stages = (kSmemLimit - 1024 - 2 * kp.region_bytes - misc) / b_stage;
     if (b_stages > kMaxBStages) b_stages = kMaxBStages;
     if (b_stages < 2) {

@@ -521,6 +521,10 @@ extern "C" int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream_v) {
                        d->cin2);
         return HG_ERR_INVALID;
     }
+    if (d->stats != nullptr && heads) {
+        set_last_error("hg_conv_nhwc_bf16: stats need a bf16 NHWC output");
+        return HG_ERR_INVALID;
+    }
     if (heads) {
         if (cout_pad > 32 || d->residual || d->up_low) {
             set_last_error("hg_conv_nhwc_bf16: fp32 NCHW output supports cout<=32 without residual terms");
@@ -619,13 +623,19 @@ extern "C" int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream_v) {
     }
 
     switch (cout_pad) {
-        case 16: return launch_conv<16, false>(kp, stream);
-        case 32: return launch_conv<32, false>(kp, stream);
-        case 64: return prologue ? launch_conv<64, true>(kp, stream) : launch_conv<64, false>(kp, stream);
-        case 128: return prologue ? launch_conv<128, true>(kp, stream) : launch_conv<128, false>(kp, stream);
-        case 256: return launch_conv<256, false>(kp, stream);
+        case 16: rc = launch_conv<16, false>(kp, stream); break;
+        case 32: rc = launch_conv<32, false>(kp, stream); break;
+        case 64: rc = prologue ? launch_conv<64, true>(kp, stream) : launch_conv<64, false>(kp, stream); break;
+        case 128: rc = prologue ? launch_conv<128, true>(kp, stream) : launch_conv<128, false>(kp, stream); break;
+        case 256: rc = launch_conv<256, false>(kp, stream); break;
         default:
             set_last_error("hg_conv_nhwc_bf16: unsupported cout_pad %d", cout_pad);
             return HG_ERR_INVALID;
     }
+    if (rc == HG_OK && d->stats != nullptr) {
+        // this general-shape kernel has no fused statistics: one pass over the (L2-resident, just written) result
+        rc = hg_colstats_nhwc(d->out, d->stats, d->stats + d->cout, static_cast<int64_t>(d->n) * d->h * d->w, d->cout, d->cout,
+                              stream_v);
+    }
+    return rc;
 }

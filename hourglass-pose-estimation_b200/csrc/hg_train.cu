@@ -15,6 +15,7 @@ namespace tr {
 
 constexpr int kThreads = 256;
 constexpr int kMaxC = 256;
+constexpr int kUnroll = 4;          // independent 128-bit loads per thread in the streaming loops
 
 static inline int grid_for(long long items, int per_sm = 8) {
     const long long cap = static_cast<long long>(num_sms()) * per_sm;
@@ -68,8 +69,26 @@ __global__ void __launch_bounds__(kThreads) colstats_kernel(const uint4* __restr
     float acc[2][8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
-    for (long long pix = static_cast<long long>(blockIdx.x) * lanes + prow; pix < pixels;
-         pix += static_cast<long long>(gridDim.x) * lanes) {
+    // kUnroll independent 16-byte loads in flight per thread: a single load per iteration leaves ~2.4 MB in flight on
+    // the whole GPU, well short of the ~6.5 MB that bandwidth x latency asks for
+    const long long stride = static_cast<long long>(gridDim.x) * lanes;
+    long long pix = static_cast<long long>(blockIdx.x) * lanes + prow;
+    for (; pix + (kUnroll - 1) * stride < pixels; pix += kUnroll * stride) {
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = ldg_nc_v4(x + (pix + u * stride) * c8 + chunk);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            float f[8];
+            unpack8(v[u], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                acc[0][e] += f[e];
+                acc[1][e] = fmaf(f[e], f[e], acc[1][e]);
+            }
+        }
+    }
+    for (; pix < pixels; pix += stride) {
         float f[8];
         unpack8(ldg_nc_v4(x + pix * c8 + chunk), f);
 #pragma unroll
@@ -132,12 +151,11 @@ __global__ void __launch_bounds__(kThreads) bn_train_fwd_kernel(const BnFwdParam
     __syncthreads();
     const long long total = pixels * p.c8;
     const int P = p.w + 1;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    auto apply = [&](long long i, const uint4& v) {
         const int chunk = static_cast<int>(i % p.c8);
         const long long pix = i / p.c8;
         float f[8];
-        unpack8(ldg_nc_v4(p.x + i), f);
+        unpack8(v, f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             f[e] = fmaf(f[e], s_scale[chunk * 8 + e], s_shift[chunk * 8 + e]);
@@ -152,7 +170,17 @@ __global__ void __launch_bounds__(kThreads) bn_train_fwd_kernel(const BnFwdParam
             o = (P + (b * (p.h + 1) + y) * P + xw) * p.c8 + chunk;
         }
         p.out[o] = pack8(f);
+    };
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    for (; i + (kUnroll - 1) * stride < total; i += kUnroll * stride) {     // kUnroll loads in flight per thread
+        uint4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = ldg_nc_v4(p.x + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) apply(i + u * stride, v[u]);
     }
+    for (; i < total; i += stride) apply(i, ldg_nc_v4(p.x + i));
 }
 
 // ---------------------------------------------------------------- BN + ReLU backward, pass 1: per-channel sums
@@ -176,8 +204,30 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const uint4* __
     float acc[2][8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
-    for (long long pix = static_cast<long long>(blockIdx.x) * lanes + prow; pix < pixels;
-         pix += static_cast<long long>(gridDim.x) * lanes) {
+    const long long stride = static_cast<long long>(gridDim.x) * lanes;
+    long long pix = static_cast<long long>(blockIdx.x) * lanes + prow;
+    constexpr int kU = 2;                  // 2 x (dz, x) = four 128-bit loads in flight
+    for (; pix + (kU - 1) * stride < pixels; pix += kU * stride) {
+        uint4 vg[kU], vx[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            vg[u] = ldg_nc_v4(dz + (pix + u * stride) * c8 + chunk);
+            vx[u] = ldg_nc_v4(x + (pix + u * stride) * c8 + chunk);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            float g[8], xv[8];
+            unpack8(vg[u], g);
+            unpack8(vx[u], xv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float dy = (!relu || fmaf(xv[e], sc[e], sh[e]) > 0.f) ? g[e] : 0.f;
+                acc[0][e] += dy;
+                acc[1][e] = fmaf(dy, (xv[e] - mean[e]) * invstd[e], acc[1][e]);
+            }
+        }
+    }
+    for (; pix < pixels; pix += stride) {
         float g[8], xv[8];
         unpack8(ldg_nc_v4(dz + pix * c8 + chunk), g);
         unpack8(ldg_nc_v4(x + pix * c8 + chunk), xv);
@@ -234,12 +284,11 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const BnBwdParam
     __syncthreads();
     const long long total = pixels * p.c8;
     const int P = p.w + 1;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    auto apply = [&](long long i, const uint4& vg, const uint4& vx) {
         const int chunk = static_cast<int>(i % p.c8);
         float g[8], xv[8], r[8];
-        unpack8(ldg_nc_v4(p.dz + i), g);
-        unpack8(ldg_nc_v4(p.x + i), xv);
+        unpack8(vg, g);
+        unpack8(vx, xv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int c = chunk * 8 + e;
@@ -268,7 +317,21 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const BnBwdParam
             o = (P + (b * (p.h + 1) + y) * P + xw) * p.c8 + chunk;
         }
         p.out[o] = pack8(r);
+    };
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    constexpr int kU = 2;                 // 2 x (dz, x) loads in flight before the dependent work (out may alias add1/add2:
+    for (; i + (kU - 1) * stride < total; i += kU * stride) {      //  those are read inside apply(), element-wise before the store)
+        uint4 vg[kU], vx[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            vg[u] = ldg_nc_v4(p.dz + i + u * stride);
+            vx[u] = ldg_nc_v4(p.x + i + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) apply(i + u * stride, vg[u], vx[u]);
     }
+    for (; i < total; i += stride) apply(i, ldg_nc_v4(p.dz + i), ldg_nc_v4(p.x + i));
 }
 
 // ---------------------------------------------------------------- max-pool 2x2 backward

@@ -25,6 +25,7 @@ class ConvDesc(C.Structure):
         ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
         ("cin", C.c_int32), ("cin2", C.c_int32), ("cout", C.c_int32),
         ("ksize", C.c_int32), ("relu", C.c_int32), ("out_halo", C.c_int32),
+        ("stats", C.c_void_p),
     ]
 
 
@@ -47,7 +48,7 @@ _SIGNATURES = {
     "hg_conv_nhwc_bf16": ([C.POINTER(ConvDesc), _vp], C.c_int),
     "hg_stem_im2col": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_halo_padded_elems": ([_i32, _i32, _i32, _i32], C.c_int64),
-    "hg_conv3x3_halo_bf16": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_conv3x3_halo_bf16": ([_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_stem_pack": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_stem_conv": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp], C.c_int),
     "hg_maxpool2x2_nhwc": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),

@@ -27,10 +27,15 @@ import torch
 # read-modify-write (accumulations): they order like writes.
 _WRITES: Dict[str, Tuple[Tuple, Tuple]] = {
     # name: (written positional indices, written keyword names)
-    "conv_nhwc": ((), ("out", "out_nchw_f32")),
-    "conv3x3_halo": ((), ("out",)),
+    "conv_nhwc": ((), ("out", "out_nchw_f32", "out_halo", "stats")),
+    "conv3x3_halo": ((), ("out", "stats")),
     "dwconv3x3": ((), ("out",)),
     "stem_im2col": ((), ("out",)),
+    "stem_pack": ((1,), ("packed",)),
+    "stem_conv": ((), ("out",)),
+    "flip_average": ((), ("out",)),
+    "decode_final_preds_into": ((3,), ("out",)),
+    "normalize_u8": ((), ("out", "packed")),
     "maxpool2x2": ((1,), ("out",)),
     "colstats": ((1, 2), ("sum_out", "sumsq_out")),
     "bn_train_fwd": ((4, 5, 6, 7, 8), ()),
@@ -87,6 +92,26 @@ def accesses(name: str, args: Sequence, kwargs: dict):
             if r is not None:
                 (writes if k in wkw else reads).append(r)
     return reads, writes
+
+
+class Recorder:
+    """Wraps a module of launch wrappers (hgb200.ops) for one eager pass: records, per call, what it reads and
+    writes.  `calls` is reset by the caller before each closure."""
+
+    def __init__(self, real):
+        self.real = real
+        self.calls: List = []
+
+    def __getattr__(self, name):
+        fn = getattr(self.real, name)
+        if not callable(fn):
+            return fn
+
+        def wrapped(*a, **k):
+            self.calls.append(accesses(name, a, k))
+            return fn(*a, **k)
+
+        return wrapped
 
 
 class _Storage:

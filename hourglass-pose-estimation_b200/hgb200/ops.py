@@ -55,13 +55,18 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
               residual: Optional[torch.Tensor] = None, up_low: Optional[torch.Tensor] = None,
               x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
               out_nchw_f32: Optional[torch.Tensor] = None, heads: bool = False,
-              out_halo: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out_halo: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Implicit-GEMM conv on tcgen05 (hg_conv_nhwc_bf16).
 
     x: bf16 [n,h,w,cin]; weight: bf16 [cout_pad, taps*cin (+cin2)]; bias fp32 [cout_pad].
     heads=True -> returns fp32 NCHW [n,cout,h,w]; else bf16 NHWC [n,h,w,cout].
+    stats: fp32 [2*cout], per-channel sum | sum of squares of the result, added by the kernel's epilogue (the
+    batch statistics of the train-mode BatchNorm that follows).
     """
-    _require_cuda(x, weight, bias, in_scale, in_shift, residual, up_low, x2, out, out_nchw_f32)
+    _require_cuda(x, weight, bias, in_scale, in_shift, residual, up_low, x2, out, out_nchw_f32, stats)
+    _check_stats(stats, cout)
+    if stats is not None and heads:
+        raise HgError("conv_nhwc: stats are for bf16 NHWC outputs")
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or (bias is not None and bias.dtype != torch.float32):
         raise HgError("conv_nhwc: x/weight must be bf16 and bias fp32")
     n, h, w, cin = x.shape
@@ -100,6 +105,7 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
     d.out = None if heads else out.data_ptr()
     d.out_nchw_f32 = out_nchw_f32.data_ptr() if heads else None
     d.err_word = err_word(x.device).data_ptr()
+    d.stats = stats.data_ptr() if stats is not None else None
     d.n, d.h, d.w, d.cin, d.cin2, d.cout, d.ksize, d.relu = n, h, w, cin, cin2, cout, ksize, int(relu)
     lib.check(lib.hg_conv_nhwc_bf16(C.byref(d), _stream()), "hg_conv_nhwc_bf16")
     return result
@@ -131,10 +137,18 @@ def halo_interior(buf: torch.Tensor, n: int, h: int, w: int, c: int) -> torch.Te
     return buf[(w + 1) * c:].view(n, h + 1, w + 1, c)[:, :h, :w, :]
 
 
+def _check_stats(stats: Optional[torch.Tensor], cout: int):
+    if stats is not None and (stats.dtype != torch.float32 or stats.numel() < 2 * cout or not stats.is_cuda):
+        raise HgError(f"stats must be a CUDA fp32 tensor of at least 2*cout = {2 * cout} elements")
+
+
 def conv3x3_halo(x_halo: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, n: int, h: int, w: int, cin: int,
-                 cout: int, relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """3x3 conv reading a halo-padded input (hg_conv3x3_halo_bf16) -> dense bf16 NHWC [n,h,w,cout]."""
-    _require_cuda(x_halo, weight, bias, out)
+                 cout: int, relu: bool = False, out: Optional[torch.Tensor] = None,
+                 stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 conv reading a halo-padded input (hg_conv3x3_halo_bf16) -> dense bf16 NHWC [n,h,w,cout].
+    stats: fp32 [2*cout], per-channel sum | sum of squares of the result, added by the kernel's epilogue."""
+    _require_cuda(x_halo, weight, bias, out, stats)
+    _check_stats(stats, cout)
     if x_halo.numel() != halo_padded_elems(n, h, w, cin) or x_halo.dtype != torch.bfloat16:
         raise HgError("conv3x3_halo: input is not a halo-padded bf16 buffer of the stated shape")
     if tuple(weight.shape) != (cout, 9 * cin) or weight.dtype != torch.bfloat16 or (bias is not None and bias.numel() < cout):
@@ -142,7 +156,7 @@ def conv3x3_halo(x_halo: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
     if out is None:
         out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x_halo.device)
     lib.check(lib.hg_conv3x3_halo_bf16(_ptr(x_halo), _ptr(weight), _ptr(bias), _ptr(out), _ptr(err_word(x_halo.device)),
-                                       n, h, w, cin, cout, int(relu), _stream()), "hg_conv3x3_halo_bf16")
+                                       _ptr(stats), n, h, w, cin, cout, int(relu), _stream()), "hg_conv3x3_halo_bf16")
     return out
 
 

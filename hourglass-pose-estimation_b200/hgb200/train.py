@@ -40,6 +40,14 @@ _ACT = torch.bfloat16     # activation / GEMM-weight storage type (the same test
 # The step's launches are captured as a dependency DAG across this many CUDA streams (hgb200/dag.py);
 # 1 = one chain on one stream.
 STREAMS = int(os.environ.get("HG_TRAIN_STREAMS", "6"))
+# HG_BN_STATS_FUSED=1: the batch statistics of a train-mode BatchNorm come out of the epilogue of the GEMM that
+# produces its input (hg_conv_desc.stats) for tensors of at most HG_BN_STATS_MAX_PIXELS pixels, instead of a separate
+# per-channel sum pass.  OFF by default -- measured on B200 (batch 32, 6 streams): 27.6 ms/step fused (32x32 and
+# below; 256 fewer launches) against 27.1 ms with the separate pass, and 29.3 ms when the 64x64 level is fused too
+# (there the four epilogue warps become the bottleneck of the HBM-bound 1x1 kernels: +9..47 us per launch against the
+# 15-20 us pass they replace).  With the launch DAG the small statistics passes already hide behind other work.
+FUSED_STATS = os.environ.get("HG_BN_STATS_FUSED", "0") == "1"
+FUSED_STATS_MAX_PIXELS = int(os.environ.get("HG_BN_STATS_MAX_PIXELS", "32768"))
 
 
 def _pad(v: int, m: int) -> int:
@@ -92,13 +100,18 @@ class ParamStore:
 
 
 class _T:
-    """An activation in the plan: bf16 NHWC data and (during backward emission) its gradient buffer."""
-    __slots__ = ("data", "grad", "grad_owned")
+    """An activation in the plan: bf16 NHWC data and (during backward emission) its gradient buffer.
+    `can_stat`: the tensor is written by a GEMM whose epilogue can add the per-channel sums a train-mode BatchNorm
+    needs; the first BatchNorm that consumes it sets `sums` (its own statistics slot) and the producer's launch --
+    which looks `sums` up when it runs -- fills it, so no separate statistics pass re-reads the tensor."""
+    __slots__ = ("data", "grad", "grad_owned", "can_stat", "sums")
 
-    def __init__(self, data):
+    def __init__(self, data, can_stat: bool = False):
         self.data = data
         self.grad = None
         self.grad_owned = True
+        self.can_stat = can_stat
+        self.sums = None
 
 
 class _Arena:
@@ -545,8 +558,15 @@ class TrainEngine:
             fwd_bytes[0] += t.numel() * 2
             return t
 
-        def bn_fwd(bn: _Bn, x, out, halo=False):
-            F.append(lambda: ops.colstats(x, bn.sums[:bn.c], bn.sums[bn.c:]))
+        def bn_fwd(bn: _Bn, x, out, halo=False, have_stats=False):
+            """relu(bn(x)) with batch statistics.  x: raw tensor (have_stats: its producer was handed bn.sums) or a _T
+            (whose producer fills the sums when it can)."""
+            if isinstance(x, _T):
+                if x.can_stat and x.sums is None:
+                    x.sums, have_stats = bn.sums, True
+                x = x.data
+            if not have_stats:
+                F.append(lambda: ops.colstats(x, bn.sums[:bn.c], bn.sums[bn.c:]))
             F.append(lambda: ops.bn_train_fwd(x, bn.sums, bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, bn.saved, out, halo=halo,
                                               relu=True, eps=bn.eps, momentum=bn.momentum))
 
@@ -558,23 +578,28 @@ class TrainEngine:
             z2h = new((nb, hh_, ww_, pl)) if blk.c2.depthwise else new_halo(nb, hh_, ww_, pl)
             a2 = new((nb, hh_, ww_, pl))
             z3 = new((nb, hh_, ww_, pl))
-            y = _T(new((nb, hh_, ww_, blk.cout)))
+            fs = FUSED_STATS and nb * hh_ * ww_ <= FUSED_STATS_MAX_PIXELS
+            y = _T(new((nb, hh_, ww_, blk.cout)), can_stat=fs)
             xd = x.data
-            bn_fwd(blk.bn1, xd, z1)
-            F.append(lambda: ops.conv_nhwc(z1, blk.c1.wf, blk.c1.b, ksize=1, cout=pl, out=a1))
+            bn_fwd(blk.bn1, x, z1)
+            F.append(lambda: ops.conv_nhwc(z1, blk.c1.wf, blk.c1.b, ksize=1, cout=pl, out=a1,
+                                           stats=blk.bn2.sums if fs else None))
             if blk.c2.depthwise:
-                bn_fwd(blk.bn2, a1, z2h)
+                bn_fwd(blk.bn2, a1, z2h, have_stats=fs)
                 F.append(lambda: ops.dwconv3x3(z2h, blk.c2.w, blk.c2.b, out=a2))
+                bn_fwd(blk.bn3, a2, z3)
             else:
-                bn_fwd(blk.bn2, a1, z2h, halo=True)
-                F.append(lambda: ops.conv3x3_halo(z2h, blk.c2.wf, blk.c2.b, n=nb, h=hh_, w=ww_, cin=pl, cout=pl, out=a2))
-            bn_fwd(blk.bn3, a2, z3)
+                bn_fwd(blk.bn2, a1, z2h, halo=True, have_stats=fs)
+                F.append(lambda: ops.conv3x3_halo(z2h, blk.c2.wf, blk.c2.b, n=nb, h=hh_, w=ww_, cin=pl, cout=pl, out=a2,
+                                                  stats=blk.bn3.sums if fs else None))
+                bn_fwd(blk.bn3, a2, z3, have_stats=fs)
             lowd = up_low.data if up_low is not None else None
             if blk.ds is not None:
-                F.append(lambda: ops.conv_nhwc(z3, blk.wf3, blk.b3, ksize=1, cout=blk.cout, x2=xd, up_low=lowd, out=y.data))
+                F.append(lambda: ops.conv_nhwc(z3, blk.wf3, blk.b3, ksize=1, cout=blk.cout, x2=xd, up_low=lowd, out=y.data,
+                                               stats=y.sums))
             else:
                 F.append(lambda: ops.conv_nhwc(z3, blk.wf3, blk.b3, ksize=1, cout=blk.cout, residual=xd, up_low=lowd,
-                                               out=y.data))
+                                               out=y.data, stats=y.sums))
             nodes.append(dict(kind="block", blk=blk, x=x, y=y, up_low=up_low, z1=z1, a1=a1, z2h=z2h, a2=a2, z3=z3))
             return y
 
@@ -600,9 +625,10 @@ class TrainEngine:
                 return chain(levels[d][0], x, up_low=low3)
             up1 = chain(levels[d][0], x)
             t = new(low3.data.shape)
-            y = _T(new(x.data.shape))
+            y = _T(new(x.data.shape), can_stat=FUSED_STATS and x.data.numel() // x.data.shape[-1] <= FUSED_STATS_MAX_PIXELS)
             F.append(lambda: ops.conv_nhwc(low3.data, cat.wfb, cat.bb, ksize=1, cout=cat.co, out=t))
-            F.append(lambda: ops.conv_nhwc(up1.data, cat.wfa, cat.ba, ksize=1, cout=cat.co, up_low=t, out=y.data))
+            F.append(lambda: ops.conv_nhwc(up1.data, cat.wfa, cat.ba, ksize=1, cout=cat.co, up_low=t, out=y.data,
+                                           stats=y.sums))
             nodes.append(dict(kind="concat", cat=cat, up1=up1, low3=low3, y=y))
             return y
 
@@ -611,8 +637,10 @@ class TrainEngine:
         a0 = new((n, h // 2, w // 2, 64))
         s0 = _T(new((n, h // 2, w // 2, 64)))
         F.append(lambda: ops.stem_im2col(plan.input, out=rows))
-        F.append(lambda: ops.conv_nhwc(rows, self.stem.wf, self.stem.b, ksize=1, cout=64, out=a0))
-        bn_fwd(self.stem_bn, a0, s0.data)
+        fs0 = FUSED_STATS and n * (h // 2) * (w // 2) <= FUSED_STATS_MAX_PIXELS
+        F.append(lambda: ops.conv_nhwc(rows, self.stem.wf, self.stem.b, ksize=1, cout=64, out=a0,
+                                       stats=self.stem_bn.sums if fs0 else None))
+        bn_fwd(self.stem_bn, a0, s0.data, have_stats=fs0)
         nodes.append(dict(kind="stem", rows=rows, a0=a0, y=s0))
         l1 = chain(self.layer1, s0)
         p1 = pool(l1)
@@ -626,8 +654,10 @@ class TrainEngine:
             nb, hh_, ww_, ch = y.data.shape
             afc = new((nb, hh_, ww_, ch))
             y2 = _T(new((nb, hh_, ww_, ch)))
-            F.append(lambda y=y, afc=afc, fcc=fcc: ops.conv_nhwc(y.data, fcc.wf, fcc.b, ksize=1, cout=ch, out=afc))
-            bn_fwd(fcb, afc, y2.data)
+            fsh = FUSED_STATS and nb * hh_ * ww_ <= FUSED_STATS_MAX_PIXELS
+            F.append(lambda y=y, afc=afc, fcc=fcc, fcb=fcb, fsh=fsh: ops.conv_nhwc(y.data, fcc.wf, fcc.b, ksize=1, cout=ch,
+                                                                                   out=afc, stats=fcb.sums if fsh else None))
+            bn_fwd(fcb, afc, y2.data, have_stats=fsh)
             nodes.append(dict(kind="fc", conv=fcc, bn=fcb, x=y, a=afc, y=y2))
             sc = self.score[i]
             F.append(lambda y2=y2, sc=sc, i=i: ops.conv_nhwc(y2.data, sc.wf, sc.b, ksize=1, cout=J, heads=True,
@@ -635,9 +665,9 @@ class TrainEngine:
             nodes.append(dict(kind="score", conv=sc, x=y2, idx=i))
             if i < self.num_stacks - 1:
                 rm = self.remap[i]
-                xn = _T(new((nb, hh_, ww_, ch)))
+                xn = _T(new((nb, hh_, ww_, ch)), can_stat=fsh)
                 F.append(lambda y2=y2, rm=rm, x=x, xn=xn: ops.conv_nhwc(y2.data, rm.wf, rm.bm, ksize=1, cout=ch,
-                                                                       residual=x.data, out=xn.data))
+                                                                       residual=x.data, out=xn.data, stats=xn.sums))
                 nodes.append(dict(kind="remap", rm=rm, x=x, y2=y2, y=xn))
                 x = xn
         plan.fwd_bytes = fwd_bytes[0]

@@ -33,7 +33,7 @@ extern "C" {
 #define HG_ERR_ARCH (-3)     /* device is not sm_100 */
 #define HG_ERR_DEVICE (-4)   /* a kernel reported a protocol timeout through its error word */
 
-#define HG_API_VERSION 3
+#define HG_API_VERSION 4
 
 int hg_api_version(void);
 /* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
@@ -74,6 +74,10 @@ typedef struct hg_conv_desc {
     int32_t relu;            /* apply ReLU in the epilogue                                      */
     int32_t out_halo;        /* 1: `out` is a HALO-PADDED buffer (see hg_conv3x3_halo_bf16); 1x1 only,
                                 needs 128 %% w == 0 and (h*w) %% 128 == 0                          */
+    float* stats;            /* optional fp32 [2*cout]: per-channel sum | sum of squares over all pixels of the
+                                epilogue's result, ADDED (atomics) -- the batch statistics the next train-mode
+                                BatchNorm needs (nn.BatchNorm2d in training, src/models/modules.py:30-41), fused
+                                into the producing GEMM so that no separate pass re-reads the tensor            */
 } hg_conv_desc;
 
 int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream);
@@ -86,7 +90,7 @@ int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream);
  * weight: bf16 [cout][9*cin], k = (ky*3+kx)*cin + c; out: dense bf16 NHWC [n][h][w][cout]; cout in {64,128}. */
 int64_t hg_halo_padded_elems(int32_t n, int32_t h, int32_t w, int32_t c);
 int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, const float* bias, void* out, unsigned int* err_word,
-                         int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t relu, void* stream);
+                         float* stats /* optional fp32 [2*cout], as hg_conv_desc.stats */, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t relu, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Input preprocessing (the step before the path).  mean3 / std3 are HOST arrays.

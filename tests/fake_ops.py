@@ -30,7 +30,7 @@ def _store(out, y_nchw):
 
 
 def conv_nhwc(x, weight, bias, *, ksize, cout, relu=False, in_scale=None, in_shift=None, residual=None, up_low=None,
-              x2=None, out=None, out_nchw_f32=None, heads=False, out_halo=None):
+              x2=None, out=None, out_nchw_f32=None, heads=False, out_halo=None, stats=None):
     n, h, w, cin = x.shape
     taps = ksize * ksize
     wm = weight.float()[:cout]
@@ -45,15 +45,18 @@ def conv_nhwc(x, weight, bias, *, ksize, cout, relu=False, in_scale=None, in_shi
         y = y + F.interpolate(_nchw(up_low), scale_factor=2, mode="nearest")
     if relu:
         y = F.relu(y)
+    if stats is not None:                 # the epilogue's fused per-channel sums of the fp32 result (before rounding)
+        stats[:cout] += y.sum((0, 2, 3))
+        stats[cout:2 * cout] += (y * y).sum((0, 2, 3))
     if heads:
         out_nchw_f32.copy_(y)
         return out_nchw_f32
     return _store(out, y)
 
 
-def conv3x3_halo(x_halo, weight, bias, *, n, h, w, cin, cout, relu=False, out=None):
+def conv3x3_halo(x_halo, weight, bias, *, n, h, w, cin, cout, relu=False, out=None, stats=None):
     x = halo_interior(x_halo, n, h, w, cin)
-    return conv_nhwc(x, weight, bias, ksize=3, cout=cout, relu=relu, out=out)
+    return conv_nhwc(x, weight, bias, ksize=3, cout=cout, relu=relu, out=out, stats=stats)
 
 
 def dwconv3x3(x, weight, bias, *, relu=False, flip=False, out=None):

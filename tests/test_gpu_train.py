@@ -141,6 +141,45 @@ def test_batchnorm_train_forward_backward(n, h, w, c, halo):
         assert bool((full == 0).all())
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,ksize,res,up", [
+    (2, 16, 16, 256, 128, 1, False, False), (3, 10, 6, 128, 256, 1, True, False), (2, 16, 16, 128, 256, 1, True, True),
+    (32, 4, 4, 256, 128, 1, False, False), (9, 64, 64, 128, 256, 1, True, False), (1, 128, 128, 192, 64, 1, False, False),
+    (2, 64, 48, 128, 256, 1, True, True),                       # general-shape kernel: statistics by a follow-up pass
+    (2, 64, 64, 128, 128, 3, False, False), (33, 4, 4, 128, 128, 3, False, False), (3, 8, 8, 64, 64, 3, False, False),
+    (5, 64, 64, 128, 128, 3, False, False)])
+def test_conv_epilogue_statistics(n, h, w, cin, cout, ksize, res, up):
+    """hg_conv_desc.stats / hg_conv3x3_halo_bf16(stats): per-channel sum and sum of squares of the convolution's fp32
+    result, added by the GEMM epilogue (the batch statistics of the BatchNorm that follows), against torch."""
+    from hgb200 import ops
+    g = torch.Generator().manual_seed(n * h + cout)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(cout, ksize, ksize, cin, generator=g) / (cin * ksize * ksize) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(cout, generator=g)
+    r = torch.randn(n, h, w, cout, generator=g).to(torch.bfloat16) if res else None
+    lo = torch.randn(n, h // 2, w // 2, cout, generator=g).to(torch.bfloat16) if up else None
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=ksize // 2)
+    if res:
+        y = y + r.float().permute(0, 3, 1, 2)
+    if up:
+        y = y + F.interpolate(lo.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    stats = torch.full((2 * cout,), 1.0, device="cuda")          # the kernel ADDS to what is there
+    wm = wt.reshape(cout, -1).cuda()
+    if ksize == 1:
+        out = ops.conv_nhwc(x.cuda(), wm, bias.cuda(), ksize=1, cout=cout, residual=r.cuda() if res else None,
+                            up_low=lo.cuda() if up else None, stats=stats)
+    else:
+        xh = ops.halo_padded_buffer(n, h, w, cin, "cuda")
+        ops.halo_interior(xh, n, h, w, cin).copy_(x.cuda())
+        out = ops.conv3x3_halo(xh, wm, bias.cuda(), n=n, h=h, w=w, cin=cin, cout=cout, stats=stats)
+    torch.cuda.synchronize()
+    ops.check_err_word()
+    assert rel(out.float().permute(0, 3, 1, 2).cpu(), y) < 1e-2
+    s1, s2 = y.sum((0, 2, 3)), (y * y).sum((0, 2, 3))
+    tol = 2e-3 if (h, w) == (64, 48) else 2e-4        # the follow-up pass sums the bf16-rounded tensor
+    assert float((stats[:cout].cpu() - 1 - s1).abs().max()) <= tol * float(s2.sqrt().max() * (n * h * w) ** 0.5)
+    assert rel(stats[cout:].cpu() - 1, s2) < max(tol, 5e-4)
+
+
 @pytest.mark.parametrize("n,h,w,c", [(2, 16, 16, 128), (3, 4, 4, 128), (1, 64, 48, 64), (2, 7, 5, 64), (33, 2, 2, 128),
                                      (1, 1, 1, 64), (2, 128, 128, 64), (1, 9, 3, 256)])
 def test_depthwise_3x3_forward_dgrad_wgrad(n, h, w, c):
@@ -230,8 +269,10 @@ def test_pack_rmsprop_small_gemm_pad():
 @pytest.mark.parametrize("S,J,B,H,W,mobile,skip", [(2, 16, 4, 128, 128, False, "sum"), (1, 17, 2, 128, 192, False, "sum"),
                                                    (2, 16, 2, 128, 128, True, "sum"), (2, 14, 2, 128, 128, True, "concat")])
 def test_every_launch_of_the_step_matches_the_emulation(monkeypatch, S, J, B, H, W, mobile, skip):
-    """tests/shadow_ops.py: each launch of the real step replayed by the CPU emulation on the same inputs."""
+    """tests/shadow_ops.py: each launch of the real step replayed by the CPU emulation on the same inputs.  The
+    mobile variants also switch the epilogue-fused BatchNorm statistics on (off by default)."""
     import hgb200.train as tr
+    monkeypatch.setattr(tr, "FUSED_STATS", bool(mobile))
     from shadow_ops import ShadowOps
     shadow = ShadowOps(tr.ops)
     monkeypatch.setattr(tr, "ops", shadow)

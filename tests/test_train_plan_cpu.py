@@ -45,6 +45,7 @@ def test_plan_is_exact_with_fp32_storage(cpu_train, monkeypatch, S, J, B, H, W, 
     from src.models import hg
     monkeypatch.setattr(cpu_train, "_ACT", torch.float32)
     monkeypatch.setattr(fake_ops, "BF", torch.float32)
+    monkeypatch.setattr(cpu_train, "FUSED_STATS", skip == "concat")     # both ways of getting the BN statistics
     sd = make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, mobile=mobile, skip_mode=skip, seed=0)
     model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=mobile, skip_mode=skip)
     model.load_state_dict(sd)
