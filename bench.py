@@ -97,6 +97,17 @@ class ClockSampler:
         return out
 
 
+def ncu_traffic(workload: str, kernel_class: str, images: int):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_ncu_traffic.json), or None when no capture matches this kernel class and batch."""
+    try:
+        with open(os.path.join(REPO, "profiles", "r1_ncu_traffic.json")) as f:
+            ent = json.load(f).get(workload, {}).get(f"{kernel_class}@{images}")
+        return ent["dram_bytes"] if ent else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def build_model(device, seed=0):
     """Random-init weights of the named architecture (torch default init, as the reference's constructor
     does) + randomised BN statistics so that folding is non-trivial."""
@@ -479,7 +490,7 @@ def main():
     else:
         roofline = {"bound": "hbm", "achieved": top["bytes"] / (avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"}
     roofline["frac"] = roofline["achieved"] / roofline["peak"]
-    roofline["traffic"] = None
+    roofline["traffic"] = ncu_traffic("infer", top_name, B)
     roofline["kernel"] = top_name
     roofline["launches_per_step"] = top["n"]
     roofline["share_of_step"] = top["ms"] / total_ms

@@ -21,6 +21,7 @@
 #include "../../include/hg_api.h"
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -42,6 +43,8 @@ struct Params {
     int H, W, P, NB;
     int cin, cout, slabs;
     int num_tiles;
+    int n_split;            // output channels are split over n_split CTAs per tile (cout = n_split * BLOCK_N): small grids
+    int num_work;           // num_tiles * n_split work items (tile-major)
     long long total_pos;    // NB*(H+1)*P  (positions after the leading zero row)
     int box_rows, num_boxes, region_bytes;   // halo'd run = num_boxes TMA boxes of box_rows rows
     int b_stages;
@@ -60,8 +63,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
     uint8_t* smem_a = smem;                                    // 2 regions
     uint8_t* smem_b = smem_a + 2 * p.region_bytes;             // b_stages x kBStage
     float* s_bias = reinterpret_cast<float*>(smem_b + p.b_stages * kBStage);
-    float* s_stats = s_bias + BLOCK_N;                          // [2*BLOCK_N]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + (kStats ? 2 * BLOCK_N : 0));
+    float* s_stats = s_bias + p.cout;                           // [2*cout]; s_bias holds all cout = n_split * BLOCK_N channels
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stats + (kStats ? 2 * p.cout : 0));
     uint64_t* a_full = bars;                  // [2]
     uint64_t* a_empty = bars + 2;             // [2]
     uint64_t* b_full = bars + 4;              // [kMaxBStages]
@@ -72,9 +75,9 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < p.cout; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
     if (kStats)
-        for (int i = threadIdx.x; i < 2 * BLOCK_N; i += blockDim.x) s_stats[i] = 0.f;
+        for (int i = threadIdx.x; i < 2 * p.cout; i += blockDim.x) s_stats[i] = 0.f;
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&p.map_a);
         tma_prefetch_desc(&p.map_b);
@@ -105,7 +108,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
             pdl_wait();
             int it = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+            for (int wi = blockIdx.x; wi < p.num_work && ok; wi += gridDim.x) {
+                const int tile = wi / p.n_split;
                 // position 0 of the tensor map is the leading zero row; tiles start after it
                 const long long f0 = static_cast<long long>(p.P) + static_cast<long long>(tile) * kBM;
                 const int row0 = static_cast<int>(f0 - halo);
@@ -126,13 +130,14 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
+            for (int wi = blockIdx.x; wi < p.num_work && ok; wi += gridDim.x) {
+                const int n0 = (wi % p.n_split) * BLOCK_N;          // this work item's output-channel window
                 for (int slab = 0; slab < p.slabs && ok; ++slab) {
                     for (int tap = 0; tap < 9; ++tap) {
                         ok = mbar_wait(&b_empty[stage], phase ^ 1u, p.err_word, 0x3301);
                         if (!ok) break;
                         mbar_arrive_expect_tx(&b_full[stage], kBStage);
-                        tma_load_2d(smem_b + stage * kBStage, &p.map_b, &b_full[stage], tap * p.cin + slab * kBlockK, 0);
+                        tma_load_2d(smem_b + stage * kBStage, &p.map_b, &b_full[stage], tap * p.cin + slab * kBlockK, n0);
                         if (++stage == p.b_stages) {
                             stage = 0;
                             phase ^= 1u;
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
             uint32_t phase = 0;
             int it = 0, a_it = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+            for (int wi = blockIdx.x; wi < p.num_work && ok; wi += gridDim.x, ++it) {
                 const int acc = it & 1;
                 ok = mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1u) ^ 1u, p.err_word, 0x3201);
                 if (!ok) break;
@@ -194,7 +199,10 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
         const long long img_pos = static_cast<long long>(p.H + 1) * p.P;
         int it = 0;
         bool ok = true;
-        for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
+        for (int wi = blockIdx.x; wi < p.num_work && ok; wi += gridDim.x, ++it) {
+            const int tile = wi / p.n_split;
+            const int n0 = (wi - tile * p.n_split) * BLOCK_N;
+            const float* bias_w = s_bias + n0;
             const int acc = it & 1;
             ok = mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1u, p.err_word, 0x3401);
             if (!ok) break;
@@ -206,7 +214,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
                 const int r = static_cast<int>(f - n * img_pos);
                 const int y = r / p.P, x = r - y * p.P;
                 const bool valid = (f < p.total_pos) && (x < p.W) && (y < p.H);
-                __nv_bfloat16* o = p.out + ((n * p.H + y) * p.W + x) * p.cout;
+                __nv_bfloat16* o = p.out + ((n * p.H + y) * p.W + x) * p.cout + n0;
                 const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                        static_cast<uint32_t>(acc * 2 * BLOCK_N + half * BLOCK_N);
 #pragma unroll
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
                                 float f8[8];
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) {
-                                    f8[j] = __uint_as_float(v[i * 8 + j]) + s_bias[c0 + i * 8 + j];
+                                    f8[j] = __uint_as_float(v[i * 8 + j]) + bias_w[c0 + i * 8 + j];
                                     if (p.relu) f8[j] = fmaxf(f8[j], 0.f);
                                 }
                                 uint4 w4;
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
                         float fv[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            fv[i] = __uint_as_float(v[i]) + s_bias[c0 + i];
+                            fv[i] = __uint_as_float(v[i]) + bias_w[c0 + i];
                             if (p.relu) fv[i] = fmaxf(fv[i], 0.f);
                         }
                         if (valid) {
@@ -264,15 +272,15 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
                         }
                         const float cs = warp_column_sum(fv, lane);
                         const float cq = warp_column_sum(sq, lane);
-                        atomicAdd(&s_stats[c0 + lane], cs);
-                        atomicAdd(&s_stats[BLOCK_N + c0 + lane], cq);
+                        atomicAdd(&s_stats[n0 + c0 + lane], cs);
+                        atomicAdd(&s_stats[p.cout + n0 + c0 + lane], cq);
                     }
                 }
             }
         }
         if (kStats) {
             named_bar_sync(1, 128);
-            for (int i = threadIdx.x - 128; i < 2 * BLOCK_N; i += 128) atomicAdd(p.stats + i, s_stats[i]);
+            for (int i = threadIdx.x - 128; i < 2 * p.cout; i += 128) atomicAdd(p.stats + i, s_stats[i]);
         }
     }
 
@@ -333,7 +341,7 @@ static int launch_variant(const Params& kp, int smem_bytes, cudaStream_t stream)
             if (dev < 64) done_mask |= 1ull << dev;
         }
     }
-    const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+    const int grid = kp.num_work < num_sms() ? kp.num_work : num_sms();
     HG_CUDA_OK(launch_kernel(kern, dim3(grid), dim3(256), smem_bytes, stream, kp));
     return HG_OK;
 }
@@ -382,7 +390,20 @@ extern "C" int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, c
     kp.num_boxes = (region_rows + 255) / 256;
     kp.box_rows = ((region_rows + kp.num_boxes - 1) / kp.num_boxes + 7) / 8 * 8;
     kp.region_bytes = kp.num_boxes * kp.box_rows * 128;
-    const int b_stage = cout * 128;
+    // Small grids (the 16x16 .. 4x4 levels of the hourglass at training batch sizes are 37 / 11 / 4 tiles): split the
+    // output channels over up to four CTAs per tile so that more SMs share the MMA work (a 256-position tile x 128
+    // channels x K=1152 is ~5 us of one SM's tensor pipe) and each CTA streams a quarter of the weights.
+    int block_n = cout;
+    if (cout == 128) {
+        const int sms = num_sms();
+        if (kp.num_tiles * 4 <= sms) block_n = 32;
+        else if (kp.num_tiles * 2 <= sms) block_n = 64;
+    }
+    static const bool no_split = getenv("HG_CONV3X3_NO_NSPLIT") != nullptr;
+    if (no_split) block_n = cout;
+    kp.n_split = cout / block_n;
+    kp.num_work = kp.num_tiles * kp.n_split;
+    const int b_stage = block_n * 128;
     const int misc = (stats ? 3 : 1) * cout * 4 + 512;
     int b_stages = (kSmemLimit - 1024 - 2 * kp.region_bytes - misc) / b_stage;
     if (b_stages > kMaxBStages) b_stages = kMaxBStages;
@@ -395,7 +416,11 @@ extern "C" int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, c
     const uint64_t rows = static_cast<uint64_t>(kp.total_pos) + kp.P;       // incl. the leading zero row
     int rc;
     if ((rc = make_map(&kp.map_a, in_padded, cin, rows, kp.box_rows)) != HG_OK) return rc;
-    if ((rc = make_map(&kp.map_b, weight, 9ull * cin, cout, cout)) != HG_OK) return rc;
+    if ((rc = make_map(&kp.map_b, weight, 9ull * cin, cout, block_n)) != HG_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    return cout == 64 ? launch<64>(kp, smem_bytes, st) : launch<128>(kp, smem_bytes, st);
+    switch (block_n) {
+        case 32: return launch<32>(kp, smem_bytes, st);
+        case 64: return launch<64>(kp, smem_bytes, st);
+        default: return launch<128>(kp, smem_bytes, st);
+    }
 }
