@@ -224,12 +224,21 @@ def build(records: Sequence) -> LaunchDag:
     return dag
 
 
-def assign_streams(dag: LaunchDag, cost: Sequence[float], k: int):
-    """-> (stream of each launch, cross-stream waits of each launch).  cost[i]: estimated duration (any unit)."""
+def assign_streams(dag: LaunchDag, cost: Sequence[float], k: int, leaf_streams: int = 0, leaf_height: float = 0.02):
+    """-> (stream of each launch, cross-stream waits of each launch).  cost[i]: estimated duration (any unit).
+
+    leaf_streams > 0 reserves the last `leaf_streams` streams for launches from which every path to a sink is short
+    (height <= leaf_height x the critical path: weight-gradient GEMMs, bias sums, the parameter-space chain rule);
+    everything else shares the first k - leaf_streams streams, which capture() can give a higher priority so that a
+    pending launch of the critical chain is scheduled before a pending leaf."""
     n = dag.n
     height = [0.0] * n                       # longest path to a sink, own cost included
     for i in range(n - 1, -1, -1):
         height[i] = cost[i] + max((height[s] for s in dag.succs[i]), default=0.0)
+    if leaf_streams <= 0 or k - leaf_streams < 1:
+        leaf_streams = 0
+    cut = leaf_height * max(height, default=0.0)
+    chain_set, leaf_set = list(range(k - leaf_streams)), list(range(k - leaf_streams, k))
     stream = [0] * n
     waits: List[List[int]] = [[] for _ in range(n)]
     tail = [-1] * k                          # last launch placed on each stream
@@ -237,28 +246,28 @@ def assign_streams(dag: LaunchDag, cost: Sequence[float], k: int):
     finish = [0.0] * n
     for i in range(n):
         preds = dag.preds[i]
+        allowed = leaf_set if (leaf_streams and height[i] <= cut) else chain_set
         ready = max((finish[p] for p in preds), default=0.0)
         choice = None
         # 1. follow a predecessor that is still the tail of its stream -- unless that predecessor has a more
         #    critical successor still to come (leave the chain to it)
         for p in sorted(preds, reverse=True):
             s = stream[p]
-            if tail[s] != p:
+            if tail[s] != p or s not in allowed:
                 continue
             rivals = [j for j in dag.succs[p] if j > i and height[j] > height[i]]
-            if rivals and k > 1:
+            if rivals and len(allowed) > 1:
                 continue
             choice = s
             break
         if choice is None:
             # 2. a stream whose tail is already an ancestor (or empty): no false edge
-            free = [s for s in range(k) if tail[s] < 0 or (dag.anc[i] >> tail[s]) & 1]
-            # keep stream 0 (origin) for launches without predecessors
+            free = [s for s in allowed if tail[s] < 0 or (dag.anc[i] >> tail[s]) & 1]
             if free:
                 choice = min(free, key=lambda s: (avail[s], s))
             else:
                 # 3. the stream that frees up first
-                choice = min(range(k), key=lambda s: (max(avail[s], ready), s))
+                choice = min(allowed, key=lambda s: (max(avail[s], ready), s))
         stream[i] = choice
         waits[i] = [p for p in preds if stream[p] != choice]
         start = max(ready, avail[choice])
@@ -268,20 +277,26 @@ def assign_streams(dag: LaunchDag, cost: Sequence[float], k: int):
     return stream, waits
 
 
-def capture(fns: Sequence[Callable], stream_of: Sequence[int], waits: Sequence[Sequence[int]], k: int, device):
-    """Capture `fns` into one CUDA graph across k streams (stream 0 = the capturing stream)."""
+def capture(fns: Sequence[Callable], stream_of: Sequence[int], waits: Sequence[Sequence[int]], k: int, device,
+            priorities: Optional[Sequence[int]] = None):
+    """Capture `fns` into one CUDA graph across k streams.  Without `priorities` stream 0 is the capturing stream;
+    with them every stream s is a fresh stream of priority priorities[s] (lower = more urgent, as CUDA counts) and the
+    capturing stream only forks and joins."""
     g = torch.cuda.CUDAGraph()
-    side = [torch.cuda.Stream(device=device) for _ in range(k - 1)]
     need_event = set()
     for w in waits:
         need_event.update(w)
     events: Dict[int, torch.cuda.Event] = {}
+    if priorities is None:
+        side = [torch.cuda.Stream(device=device) for _ in range(k - 1)]
+    else:
+        side = [torch.cuda.Stream(device=device, priority=int(priorities[s])) for s in range(k)]
     with torch.cuda.graph(g):
         origin = torch.cuda.current_stream(device)
-        streams = [origin] + side
+        streams = ([origin] + side) if priorities is None else side
         start = torch.cuda.Event()
         start.record(origin)
-        joined = [True] + [False] * (k - 1)
+        joined = [st is origin for st in streams]
         for i, fn in enumerate(fns):
             s = stream_of[i]
             st = streams[s]
@@ -296,8 +311,8 @@ def capture(fns: Sequence[Callable], stream_of: Sequence[int], waits: Sequence[S
                 ev = torch.cuda.Event()
                 ev.record(st)
                 events[i] = ev
-        for s in range(1, k):                    # join everything back into the origin stream
-            if joined[s]:
+        for s in range(k):                       # join everything back into the origin stream
+            if joined[s] and streams[s] is not origin:
                 ev = torch.cuda.Event()
                 ev.record(streams[s])
                 origin.wait_event(ev)

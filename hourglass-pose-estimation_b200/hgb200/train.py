@@ -39,7 +39,10 @@ _TEST_ALLOW_CPU = False
 _ACT = torch.bfloat16     # activation / GEMM-weight storage type (the same test switches it to fp32 for exact checks)
 # The step's launches are captured as a dependency DAG across this many CUDA streams (hgb200/dag.py);
 # 1 = one chain on one stream.
-STREAMS = int(os.environ.get("HG_TRAIN_STREAMS", "6"))
+STREAMS = int(os.environ.get("HG_TRAIN_STREAMS", "8"))
+# ... of which this many are reserved for the leaves of the DAG (weight-gradient GEMMs, bias sums) and run at normal
+# priority while the streams carrying the critical chain get CUDA's high priority (0 = no separation).
+LEAF_STREAMS = int(os.environ.get("HG_TRAIN_LEAF_STREAMS", "0"))
 # HG_BN_STATS_FUSED=1: the batch statistics of a train-mode BatchNorm come out of the epilogue of the GEMM that
 # produces its input (hg_conv_desc.stats) for tensors of at most HG_BN_STATS_MAX_PIXELS pixels, instead of a separate
 # per-channel sum pass.  OFF by default -- measured on B200 (batch 32, 6 streams): 27.6 ms/step fused (32x32 and
@@ -440,7 +443,7 @@ class TrainPlan:
             lo, hi = self._slice(which)
             d = dag.build(self.records[lo:hi])
             cost = [4e-6 + max(m["flops"] / 6e14, m["bytes"] / 3e12) for m in self.meta[lo:hi]]
-            stream_of, waits = dag.assign_streams(d, cost, k)
+            stream_of, waits = dag.assign_streams(d, cost, k, leaf_streams=LEAF_STREAMS)
             sched = self.schedules[(which, k)] = (d, stream_of, waits)
         return sched
 
@@ -450,7 +453,10 @@ class TrainPlan:
         fns = self.launches(which)
         if STREAMS > 1:
             _, stream_of, waits = self.schedule(which)
-            g = dag.capture(fns, stream_of, waits, STREAMS, self.eng.device)
+            prio = None
+            if LEAF_STREAMS > 0 and STREAMS - LEAF_STREAMS >= 1:
+                prio = [-1] * (STREAMS - LEAF_STREAMS) + [0] * LEAF_STREAMS
+            g = dag.capture(fns, stream_of, waits, STREAMS, self.eng.device, priorities=prio)
         else:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

@@ -1,5 +1,4 @@
-python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py tests/test_gpu_train.py -x -q > gpurun_out/pytest_nsplit.log 2>&1; echo "exit $?"; tail -5 gpurun_out/pytest_nsplit.log
-python bench.py --workload train --steps 10 --warmup 3 --no-cpu-baseline --breakdown gpurun_out/train_breakdown_nsplit.csv > gpurun_out/bench_train_nsplit.json 2> gpurun_out/bench_train_nsplit.err; echo "exit $?"; cut -c1-220 gpurun_out/bench_train_nsplit.json
-HG_CONV3X3_NO_NSPLIT=1 python bench.py --workload train --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_train_nonsplit.json 2> gpurun_out/bench_train_nonsplit.err; echo "exit $?"; cut -c1-220 gpurun_out/bench_train_nonsplit.json
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_infer_nsplit.json 2> gpurun_out/bench_infer_nsplit.err; echo "exit $?"; cut -c1-220 gpurun_out/bench_infer_nsplit.json
-HG_CONV3X3_NO_NSPLIT=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_infer_nonsplit.json 2> gpurun_out/bench_infer_nonsplit.err; echo "exit $?"; cut -c1-220 gpurun_out/bench_infer_nonsplit.json
+for w in 32 16 8 4; do
+HG_HALO_MIN_W=$w python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_infer_halo$w.json 2> gpurun_out/bench_infer_halo$w.err; echo "halo_min_w $w exit $?"; python -c "
+import json; d=json.loads(open('gpurun_out/bench_infer_halo$w.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['clocks'])"
+done
