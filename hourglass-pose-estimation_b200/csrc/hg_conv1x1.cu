@@ -10,6 +10,11 @@
 //   * pre-activation bn1+ReLU prologue with a conflict-free mapping (a quarter-warp owns one
 //     128-byte row; per-thread channel chunk is fixed so scale/shift live in registers per k-block).
 //
+//   * optional second output: the 2x2 max-pool of the result (the hourglass pools every level's input,
+//     src/models/modules.py:82): a 128-pixel tile holds whole pooling windows, so the epilogue takes the maximum of
+//     four rows of the bf16 slab it has just staged and TMA-stores a 32-row slab of the pooled tensor -- the pool
+//     kernel's full re-read of the 256-channel tensor disappears.
+//
 // Warp roles: 0 = A producer (TMA), 1 = MMA issuer + TMEM owner, 2 = staging-ring producer (TMA),
 //             3 = idle, 4..7 = epilogue, 8..11 = prologue (optional).
 #include "hg_common.cuh"
@@ -40,6 +45,7 @@ struct Params {
     CUtensorMap map_res;    // (c, m) over residual
     CUtensorMap map_up;     // (c, m/4) over the quarter-resolution tensor
     CUtensorMap map_out;    // (c, m) over out
+    CUtensorMap map_pool;   // (c, m/4) over the max-pooled output (kPool)
     const float* bias;
     const float* in_scale;
     const float* in_shift;
@@ -51,6 +57,7 @@ struct Params {
     int cin;
     int a_stages, ring;     // pipeline depths chosen by the host from the smem budget
     int has_res, has_up, relu;
+    int has_pool;           // image width when the 2x2 max-pool of the result is written too (kPool), else 0
     int out_halo, img_h, img_w;     // out_halo: map_out is the 4-D strided view (c, x, y, n) of a halo-padded buffer
 };
 
@@ -61,7 +68,13 @@ __host__ __device__ constexpr int w_bytes(int num_kb) { return num_kb * BLOCK_N 
 
 // kStats: the epilogue also adds the per-channel sum / sum of squares of its results into p.stats.  A separate
 // instantiation so that the plain kernel (inference, dgrad) keeps its register budget and schedule.
-template <int BLOCK_N, bool kPrologue, bool kStats>
+__device__ __forceinline__ uint32_t bf16x2_max_u32(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// kPool: the epilogue also writes the 2x2 max-pool of its result through p.map_pool.
+template <int BLOCK_N, bool kPrologue, bool kStats, bool kPool>
 __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const __grid_constant__ Params p) {
     constexpr int kBStage = BLOCK_N * kBlockK * 2;
     constexpr int kSlabs = BLOCK_N / 64;
@@ -74,7 +87,8 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
     uint8_t* smem_a = smem_w + num_kb * kBStage;                   // a_stages x 16 KiB
     uint8_t* smem_ring = smem_a + p.a_stages * kSlabBytes;         // ring x 16 KiB
     uint8_t* smem_up = smem_ring + p.ring * kSlabBytes;            // ring x 4 KiB (only if has_up)
-    float* s_bias = reinterpret_cast<float*>(smem_up + (p.has_up ? p.ring * kUpBytes : 0));
+    uint8_t* smem_pool = smem_up + (p.has_up ? p.ring * kUpBytes : 0);     // 2 x 4 KiB pooled staging slabs (kPool)
+    float* s_bias = reinterpret_cast<float*>(smem_pool + (kPool ? 2 * kUpBytes : 0));
     float* s_stats = s_bias + BLOCK_N;                             // [2*BLOCK_N] column sums of this CTA's tiles
     float* s_scale = s_stats + (kStats ? 2 * BLOCK_N : 0);
     float* s_shift = s_scale + (kPrologue ? kMaxK : 0);
@@ -108,6 +122,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
         if (p.kb2) tma_prefetch_desc(&p.map_a2);
         if (p.has_res) tma_prefetch_desc(&p.map_res);
         if (p.has_up) tma_prefetch_desc(&p.map_up);
+        if (kPool) tma_prefetch_desc(&p.map_pool);
         for (int s = 0; s < kMaxAStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -239,6 +254,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
         int buf = 0;
         uint32_t ring_phase = 0;
         int prev_buf = -1;
+        int pool_it = 0;
         bool ok = true;
         for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -343,7 +359,37 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                 }
                 fence_proxy_async_smem();
                 named_bar_sync(1, 128);
+                if (kPool) {
+                    // 2x2 max-pool of the staged slab: 32 pooled pixels x 8 sixteen-byte chunks = 2 items per thread
+                    const uint32_t slab_s = smem_u32(smem_ring + buf * kSlabBytes);
+                    const uint32_t pool_s = smem_u32(smem_pool + (pool_it & 1) * kUpBytes);
+                    const int W = p.has_pool, Wh = W >> 1;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int item = static_cast<int>(threadIdx.x) - 128 + 128 * k;
+                        const int prow = item >> 3, chunk = item & 7;
+                        const int py = prow / Wh, px = prow - py * Wh;
+                        const int r0 = 2 * py * W + 2 * px;
+                        const int rr[4] = {r0, r0 + 1, r0 + W, r0 + W + 1};
+                        uint4 m = lds128(slab_s + rr[0] * 128 + ((chunk ^ (rr[0] & 7)) << 4));
+#pragma unroll
+                        for (int j = 1; j < 4; ++j) {
+                            const uint4 v4 = lds128(slab_s + rr[j] * 128 + ((chunk ^ (rr[j] & 7)) << 4));
+                            m.x = bf16x2_max_u32(m.x, v4.x);
+                            m.y = bf16x2_max_u32(m.y, v4.y);
+                            m.z = bf16x2_max_u32(m.z, v4.z);
+                            m.w = bf16x2_max_u32(m.w, v4.w);
+                        }
+                        sts128(pool_s + prow * 128 + ((chunk ^ (prow & 7)) << 4), m);
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                }
                 if (leader) {
+                    if (kPool) {
+                        // same bulk group as the slab's own store: the read-completion wait below covers both
+                        tma_store_2d(&p.map_pool, smem_pool + (pool_it & 1) * kUpBytes, slab * 64, m0 >> 2);
+                    }
                     if (p.out_halo) {
                         const int hw = p.img_h * p.img_w;
                         const int n_img = m0 / hw;
@@ -359,6 +405,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                     }
                 }
                 prev_buf = buf;
+                if (kPool) ++pool_it;
                 if (++buf == p.ring) {
                     buf = 0;
                     ring_phase ^= 1u;
@@ -461,9 +508,9 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t r
     return HG_OK;
 }
 
-template <int BLOCK_N, bool kPrologue, bool kStats>
+template <int BLOCK_N, bool kPrologue, bool kStats, bool kPool = false>
 static int launch_variant(const Params& kp, int smem_bytes, cudaStream_t stream) {
-    auto kern = conv1x1_kernel<BLOCK_N, kPrologue, kStats>;
+    auto kern = conv1x1_kernel<BLOCK_N, kPrologue, kStats, kPool>;
     static std::mutex mu;
     static unsigned long long done_mask = 0;
     int dev = 0;
@@ -498,6 +545,16 @@ int conv1x1_supported(const hg_conv_desc* d) {
     if (d->out_halo) {
         if (d->w > 128 || 128 % d->w != 0 || (static_cast<long long>(d->h) * d->w) % 128 != 0) return 0;
     }
+    if (d->pool_out != nullptr) {
+        // the fused max-pool output: 256-channel results without prologue / statistics, whole 2x2 windows per tile
+        const int w = d->w, h = d->h;
+        const bool pow2 = (w & (w - 1)) == 0;
+        if (d->cout != 256 || d->in_scale != nullptr || d->stats != nullptr || d->out_halo) return 0;
+        // K <= 128 only: with K = 256 the resident weights (128 KiB) leave no room for the two pooled staging slabs without
+        // shrinking the staging ring, and the kernel loses more than the pool pass costs (measured: 481 vs 284 + 110 us)
+        if (d->cin + d->cin2 > 128) return 0;
+        if (!pow2 || w > 64 || w < 2 || (h & 1) || 128 % (2 * w) != 0) return 0;
+    }
     if (d->up_low != nullptr) {
         // the TMA-fed upsample operand needs whole 2x2 blocks inside every 128-pixel tile
         const int w = d->w, h = d->h;
@@ -530,12 +587,14 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
     kp.cin = d->cin;
     kp.has_res = d->residual != nullptr;
     kp.has_up = d->up_low != nullptr ? d->w : 0;
+    kp.has_pool = d->pool_out != nullptr ? d->w : 0;
     kp.relu = d->relu;
 
     // shared-memory budget -> pipeline depths
     const int num_kb = kp.kb1 + kp.kb2;
     const int wbytes = num_kb * d->cout * kBlockK * 2;
-    const int misc = (d->stats ? 3 : 1) * d->cout * 4 + (prologue ? 2 * kMaxK * 4 : 0) + 512;   // bias, column sums, scale/shift, barriers
+    const int misc = (d->stats ? 3 : 1) * d->cout * 4 + (prologue ? 2 * kMaxK * 4 : 0) + 512 +   // bias, column sums, scale/shift, barriers
+                     (d->pool_out ? 2 * kUpBytes : 0);                                          // pooled staging slabs
     int avail = kSmemLimit - 1024 - wbytes - misc;
     const int ring_unit = kSlabBytes + (kp.has_up ? kUpBytes : 0);
     const int slabs = d->cout / 64;
@@ -584,6 +643,10 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
     }
     if (d->residual && (rc = make_map(&kp.map_res, d->residual, d->cout, m, kTileM)) != HG_OK) return rc;
     if (d->up_low && (rc = make_map(&kp.map_up, d->up_low, d->cout, m / 4, kUpRows)) != HG_OK) return rc;
+    if (d->pool_out) {
+        if ((rc = make_map(&kp.map_pool, d->pool_out, d->cout, m / 4, kUpRows)) != HG_OK) return rc;
+        return launch_variant<256, false, false, true>(kp, smem_bytes, stream);
+    }
 
     switch (d->cout) {
         case 64: return prologue ? launch<64, true>(kp, smem_bytes, stream) : launch<64, false>(kp, smem_bytes, stream);

@@ -550,6 +550,11 @@ extern "C" int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream_v) {
         if (!force_generic && conv1x1_supported(d)) return conv1x1_launch(d, stream);
     }
 
+    if (d->pool_out) {
+        set_last_error("hg_conv_nhwc_bf16: pool_out needs a 1x1 conv with cout 256, no prologue / stats / out_halo, w a power of two "
+                       "<= 64 with 128 %% (2*w) == 0 and even h");
+        return HG_ERR_INVALID;
+    }
     if (d->out_halo) {
         set_last_error("hg_conv_nhwc_bf16: out_halo needs a 1x1 conv with 128 %% w == 0, (h*w) %% 128 == 0, cout in {64,128,256}");
         return HG_ERR_INVALID;

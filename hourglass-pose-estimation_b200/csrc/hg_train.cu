@@ -15,7 +15,8 @@ namespace tr {
 
 constexpr int kThreads = 256;
 constexpr int kMaxC = 256;
-constexpr int kUnroll = 4;          // independent 128-bit loads per thread in the streaming loops
+constexpr int kUnroll = 4;          // independent 128-bit loads per thread in the streaming loops (8 measured slower:
+                                    // 27.9 vs 26.5 ms/step -- registers cost occupancy)
 
 static inline int grid_for(long long items, int per_sm = 8) {
     const long long cap = static_cast<long long>(num_sms()) * per_sm;

@@ -27,7 +27,7 @@ import torch
 # read-modify-write (accumulations): they order like writes.
 _WRITES: Dict[str, Tuple[Tuple, Tuple]] = {
     # name: (written positional indices, written keyword names)
-    "conv_nhwc": ((), ("out", "out_nchw_f32", "out_halo", "stats")),
+    "conv_nhwc": ((), ("out", "out_nchw_f32", "out_halo", "stats", "pool_out")),
     "conv3x3_halo": ((), ("out", "stats")),
     "dwconv3x3": ((), ("out",)),
     "stem_im2col": ((), ("out",)),

@@ -33,6 +33,9 @@ from .fold import NetWeights, BlockWeights
 # is nothing to overlap with; the default stays one chain on one stream (the training step, whose launches are
 # small, gains 18 % from the same machinery).
 STREAMS = int(os.environ.get("HG_INFER_STREAMS", "1"))
+# The 2x2 max-pool of a hourglass level's input is written by the epilogue of the 1x1 GEMM that produces that input
+# (hg_conv_desc.pool_out) instead of a separate kernel that re-reads it; HG_NO_POOL_FUSION=1 keeps the separate kernel.
+FUSE_POOL = os.environ.get("HG_NO_POOL_FUSION", "0") != "1"
 
 
 class _Arena:
@@ -45,13 +48,17 @@ class _Arena:
         self.free = defaultdict(list)
         self.total_bytes = 0
         self.depth = depth
+        self.on_get = None
 
     def get(self, shape, dtype=torch.bfloat16) -> torch.Tensor:
         key = (tuple(shape), dtype)
         if len(self.free[key]) >= self.depth:
-            return self.free[key].pop(0)
-        t = torch.empty(shape, dtype=dtype, device=self.device)
-        self.total_bytes += t.numel() * t.element_size()
+            t = self.free[key].pop(0)
+        else:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.total_bytes += t.numel() * t.element_size()
+        if self.on_get is not None:
+            self.on_get(t)                   # a re-issued buffer forgets what was recorded about its previous content
         return t
 
     def put(self, t: torch.Tensor):
@@ -206,6 +213,9 @@ class HourglassEngine:
         both = (flip == 'both')
         nb = 2 * n if both else n           # rows the network sees
         halo_min_w = int(os.environ.get("HG_HALO_MIN_W", "32"))   # levels at least this wide use the halo 3x3 kernel
+        producer: Dict[int, int] = {}       # data_ptr of a fusable 1x1 conv's output -> index of its launch
+        pool_targets: Dict[int, torch.Tensor] = {}
+        arena.on_get = lambda t: producer.pop(t.data_ptr(), None)
 
         def conv(x, wt, bias, *, ksize, cout, relu=False, in_scale=None, in_shift=None, residual=None, up_low=None,
                  x2=None, out_f32=None):
@@ -227,8 +237,13 @@ class HourglassEngine:
                                                out_nchw_f32=out_f32))
                 return out_f32
             out = arena.get((*shape, cout))
+            idx = len(L)
+            # a later pool(out) may attach its output to THIS launch (pool_targets[idx], looked up when the launch runs)
+            if (FUSE_POOL and ksize == 1 and in_scale is None and ops.conv_pool_fusable(shape[1], shape[2], cout, ktot)):
+                producer[out.data_ptr()] = idx
             L.append(lambda: ops.conv_nhwc(x, wt, bias, ksize=ksize, cout=cout, relu=relu, in_scale=in_scale,
-                                           in_shift=in_shift, residual=residual, up_low=up_low, x2=x2, out=out))
+                                           in_shift=in_shift, residual=residual, up_low=up_low, x2=x2, out=out,
+                                           pool_out=pool_targets.get(idx)))
             return out
 
         def block(bw: BlockWeights, x, up_low=None):
@@ -282,6 +297,14 @@ class HourglassEngine:
         def pool(x):
             nb, hh, ww, c = x.shape
             out = arena.get((nb, hh // 2, ww // 2, c))
+            idx = producer.pop(x.data_ptr(), None)
+            if idx is not None:
+                # the 1x1 GEMM that produced x writes the pooled tensor from its own epilogue: no pool launch, and the
+                # full re-read of x disappears
+                pool_targets[idx] = out
+                plan.meta[idx]["op"] += "_pool"
+                plan.meta[idx]["bytes"] += out.numel() * 2
+                return out
             plan.meta.append(dict(op=f"maxpool_{hh}x{ww}_c{c}", kind="bw", flops=0.0, bytes=x.numel() * 2 * 1.25))
             L.append(lambda: ops.maxpool2x2(x, out))
             return out

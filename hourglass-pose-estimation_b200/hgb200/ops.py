@@ -55,18 +55,28 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
               residual: Optional[torch.Tensor] = None, up_low: Optional[torch.Tensor] = None,
               x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
               out_nchw_f32: Optional[torch.Tensor] = None, heads: bool = False,
-              out_halo: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out_halo: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
+              pool_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Implicit-GEMM conv on tcgen05 (hg_conv_nhwc_bf16).
 
     x: bf16 [n,h,w,cin]; weight: bf16 [cout_pad, taps*cin (+cin2)]; bias fp32 [cout_pad].
     heads=True -> returns fp32 NCHW [n,cout,h,w]; else bf16 NHWC [n,h,w,cout].
     stats: fp32 [2*cout], per-channel sum | sum of squares of the result, added by the kernel's epilogue (the
     batch statistics of the train-mode BatchNorm that follows).
+    pool_out: bf16 [n,h/2,w/2,cout], additionally receives max_pool2d(result, 2, 2) from the same epilogue
+    (see conv_pool_fusable).
     """
     _require_cuda(x, weight, bias, in_scale, in_shift, residual, up_low, x2, out, out_nchw_f32, stats)
     _check_stats(stats, cout)
     if stats is not None and heads:
         raise HgError("conv_nhwc: stats are for bf16 NHWC outputs")
+    if pool_out is not None:
+        _require_cuda(pool_out)
+        if (not conv_pool_fusable(x.shape[1], x.shape[2], cout, weight.shape[1]) or ksize != 1 or heads or in_scale is not None
+                or stats is not None or out_halo is not None):
+            raise HgError("conv_nhwc: pool_out needs a plain 1x1 conv with cout 256 on a level conv_pool_fusable() accepts")
+        if tuple(pool_out.shape) != (x.shape[0], x.shape[1] // 2, x.shape[2] // 2, cout) or pool_out.dtype != torch.bfloat16:
+            raise HgError("conv_nhwc: pool_out must be bf16 [n,h/2,w/2,cout]")
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or (bias is not None and bias.dtype != torch.float32):
         raise HgError("conv_nhwc: x/weight must be bf16 and bias fp32")
     n, h, w, cin = x.shape
@@ -106,9 +116,17 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
     d.out_nchw_f32 = out_nchw_f32.data_ptr() if heads else None
     d.err_word = err_word(x.device).data_ptr()
     d.stats = stats.data_ptr() if stats is not None else None
+    d.pool_out = pool_out.data_ptr() if pool_out is not None else None
     d.n, d.h, d.w, d.cin, d.cin2, d.cout, d.ksize, d.relu = n, h, w, cin, cin2, cout, ksize, int(relu)
     lib.check(lib.hg_conv_nhwc_bf16(C.byref(d), _stream()), "hg_conv_nhwc_bf16")
     return result
+
+
+def conv_pool_fusable(h: int, w: int, cout: int, k: int) -> bool:
+    """Whether hg_conv_nhwc_bf16 can also write the 2x2 max-pool of a 1x1 conv's [n,h,w,cout] result (pool_out): a
+    128-pixel tile must hold whole pooling windows, and K = cin (+cin2) <= 128 so that the pooled staging slabs fit
+    beside the resident weights without shrinking the staging ring."""
+    return cout == 256 and k <= 128 and 2 <= w <= 64 and (w & (w - 1)) == 0 and h % 2 == 0 and 128 % (2 * w) == 0
 
 
 def stem_im2col(x_nchw: torch.Tensor, flip_w: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:

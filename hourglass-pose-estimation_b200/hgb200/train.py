@@ -50,6 +50,9 @@ LEAF_STREAMS = int(os.environ.get("HG_TRAIN_LEAF_STREAMS", "0"))
 # (there the four epilogue warps become the bottleneck of the HBM-bound 1x1 kernels: +9..47 us per launch against the
 # 15-20 us pass they replace).  With the launch DAG the small statistics passes already hide behind other work.
 FUSED_STATS = os.environ.get("HG_BN_STATS_FUSED", "0") == "1"
+# The 2x2 max-pool of a hourglass level's input comes out of the epilogue of the 1x1 GEMM that produces that input
+# (hg_conv_desc.pool_out); HG_NO_POOL_FUSION=1 keeps the separate pool kernel.
+FUSE_POOL = os.environ.get("HG_NO_POOL_FUSION", "0") != "1"
 FUSED_STATS_MAX_PIXELS = int(os.environ.get("HG_BN_STATS_MAX_PIXELS", "32768"))
 
 
@@ -106,15 +109,19 @@ class _T:
     """An activation in the plan: bf16 NHWC data and (during backward emission) its gradient buffer.
     `can_stat`: the tensor is written by a GEMM whose epilogue can add the per-channel sums a train-mode BatchNorm
     needs; the first BatchNorm that consumes it sets `sums` (its own statistics slot) and the producer's launch --
-    which looks `sums` up when it runs -- fills it, so no separate statistics pass re-reads the tensor."""
-    __slots__ = ("data", "grad", "grad_owned", "can_stat", "sums")
+    which looks `sums` up when it runs -- fills it, so no separate statistics pass re-reads the tensor.
+    `can_pool` / `pool_out`: likewise for the 2x2 max-pool of the tensor (hg_conv_desc.pool_out): pool() sets pool_out
+    and emits no launch of its own."""
+    __slots__ = ("data", "grad", "grad_owned", "can_stat", "sums", "can_pool", "pool_out")
 
-    def __init__(self, data, can_stat: bool = False):
+    def __init__(self, data, can_stat: bool = False, can_pool: bool = False):
         self.data = data
         self.grad = None
         self.grad_owned = True
         self.can_stat = can_stat
         self.sums = None
+        self.can_pool = can_pool
+        self.pool_out = None
 
 
 class _Arena:
@@ -568,7 +575,7 @@ class TrainEngine:
             """relu(bn(x)) with batch statistics.  x: raw tensor (have_stats: its producer was handed bn.sums) or a _T
             (whose producer fills the sums when it can)."""
             if isinstance(x, _T):
-                if x.can_stat and x.sums is None:
+                if x.can_stat and x.sums is None and x.pool_out is None:
                     x.sums, have_stats = bn.sums, True
                 x = x.data
             if not have_stats:
@@ -585,7 +592,8 @@ class TrainEngine:
             a2 = new((nb, hh_, ww_, pl))
             z3 = new((nb, hh_, ww_, pl))
             fs = FUSED_STATS and nb * hh_ * ww_ <= FUSED_STATS_MAX_PIXELS
-            y = _T(new((nb, hh_, ww_, blk.cout)), can_stat=fs)
+            y = _T(new((nb, hh_, ww_, blk.cout)), can_stat=fs,
+                   can_pool=FUSE_POOL and not fs and ops.conv_pool_fusable(hh_, ww_, blk.cout, pl + (cin if blk.ds is not None else 0)))
             xd = x.data
             bn_fwd(blk.bn1, x, z1)
             F.append(lambda: ops.conv_nhwc(z1, blk.c1.wf, blk.c1.b, ksize=1, cout=pl, out=a1,
@@ -602,10 +610,10 @@ class TrainEngine:
             lowd = up_low.data if up_low is not None else None
             if blk.ds is not None:
                 F.append(lambda: ops.conv_nhwc(z3, blk.wf3, blk.b3, ksize=1, cout=blk.cout, x2=xd, up_low=lowd, out=y.data,
-                                               stats=y.sums))
+                                               stats=y.sums, pool_out=y.pool_out))
             else:
                 F.append(lambda: ops.conv_nhwc(z3, blk.wf3, blk.b3, ksize=1, cout=blk.cout, residual=xd, up_low=lowd,
-                                               out=y.data, stats=y.sums))
+                                               out=y.data, stats=y.sums, pool_out=y.pool_out))
             nodes.append(dict(kind="block", blk=blk, x=x, y=y, up_low=up_low, z1=z1, a1=a1, z2h=z2h, a2=a2, z3=z3))
             return y
 
@@ -618,7 +626,11 @@ class TrainEngine:
         def pool(x: _T) -> _T:
             nb, hh_, ww_, c = x.data.shape
             p = _T(new((nb, hh_ // 2, ww_ // 2, c)))
-            F.append(lambda: ops.maxpool2x2(x.data, p.data))
+            if x.can_pool and x.pool_out is None and x.sums is None:
+                x.pool_out = p.data          # x's producer (looked up when it runs) writes the pooled tensor itself
+                x.can_stat = False           # the kernel does one or the other
+            else:
+                F.append(lambda: ops.maxpool2x2(x.data, p.data))
             nodes.append(dict(kind="pool", x=x, y=p))
             return p
 
@@ -631,10 +643,12 @@ class TrainEngine:
                 return chain(levels[d][0], x, up_low=low3)
             up1 = chain(levels[d][0], x)
             t = new(low3.data.shape)
-            y = _T(new(x.data.shape), can_stat=FUSED_STATS and x.data.numel() // x.data.shape[-1] <= FUSED_STATS_MAX_PIXELS)
+            fsc = FUSED_STATS and x.data.numel() // x.data.shape[-1] <= FUSED_STATS_MAX_PIXELS
+            y = _T(new(x.data.shape), can_stat=fsc,
+                   can_pool=FUSE_POOL and not fsc and ops.conv_pool_fusable(x.data.shape[1], x.data.shape[2], cat.co, cat.cig))
             F.append(lambda: ops.conv_nhwc(low3.data, cat.wfb, cat.bb, ksize=1, cout=cat.co, out=t))
             F.append(lambda: ops.conv_nhwc(up1.data, cat.wfa, cat.ba, ksize=1, cout=cat.co, up_low=t, out=y.data,
-                                           stats=y.sums))
+                                           stats=y.sums, pool_out=y.pool_out))
             nodes.append(dict(kind="concat", cat=cat, up1=up1, low3=low3, y=y))
             return y
 
@@ -671,9 +685,11 @@ class TrainEngine:
             nodes.append(dict(kind="score", conv=sc, x=y2, idx=i))
             if i < self.num_stacks - 1:
                 rm = self.remap[i]
-                xn = _T(new((nb, hh_, ww_, ch)), can_stat=fsh)
+                xn = _T(new((nb, hh_, ww_, ch)), can_stat=fsh,
+                        can_pool=FUSE_POOL and not fsh and ops.conv_pool_fusable(hh_, ww_, ch, ch))
                 F.append(lambda y2=y2, rm=rm, x=x, xn=xn: ops.conv_nhwc(y2.data, rm.wf, rm.bm, ksize=1, cout=ch,
-                                                                       residual=x.data, out=xn.data, stats=xn.sums))
+                                                                       residual=x.data, out=xn.data, stats=xn.sums,
+                                                                       pool_out=xn.pool_out))
                 nodes.append(dict(kind="remap", rm=rm, x=x, y2=y2, y=xn))
                 x = xn
         plan.fwd_bytes = fwd_bytes[0]

@@ -33,7 +33,7 @@ extern "C" {
 #define HG_ERR_ARCH (-3)     /* device is not sm_100 */
 #define HG_ERR_DEVICE (-4)   /* a kernel reported a protocol timeout through its error word */
 
-#define HG_API_VERSION 4
+#define HG_API_VERSION 5
 
 int hg_api_version(void);
 /* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
@@ -78,6 +78,10 @@ typedef struct hg_conv_desc {
                                 epilogue's result, ADDED (atomics) -- the batch statistics the next train-mode
                                 BatchNorm needs (nn.BatchNorm2d in training, src/models/modules.py:30-41), fused
                                 into the producing GEMM so that no separate pass re-reads the tensor            */
+    void* pool_out;          /* optional second output: F.max_pool2d(out, 2, stride=2) as bf16 NHWC [n][h/2][w/2][cout]
+                                (the hourglass pools every level's input, src/models/modules.py:82), written by the
+                                same epilogue.  1x1 only: cout 256, cin + cin2 <= 128, no prologue / stats / out_halo,
+                                w a power of two <= 64 with 128 %% (2*w) == 0, even h                              */
 } hg_conv_desc;
 
 int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream);

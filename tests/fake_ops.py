@@ -30,7 +30,7 @@ def _store(out, y_nchw):
 
 
 def conv_nhwc(x, weight, bias, *, ksize, cout, relu=False, in_scale=None, in_shift=None, residual=None, up_low=None,
-              x2=None, out=None, out_nchw_f32=None, heads=False, out_halo=None, stats=None):
+              x2=None, out=None, out_nchw_f32=None, heads=False, out_halo=None, stats=None, pool_out=None):
     n, h, w, cin = x.shape
     taps = ksize * ksize
     wm = weight.float()[:cout]
@@ -51,7 +51,14 @@ def conv_nhwc(x, weight, bias, *, ksize, cout, relu=False, in_scale=None, in_shi
     if heads:
         out_nchw_f32.copy_(y)
         return out_nchw_f32
-    return _store(out, y)
+    _store(out, y)
+    if pool_out is not None:              # the 2x2 max-pool of the STORED (rounded) result
+        _store(pool_out, F.max_pool2d(_nchw(out), 2, 2))
+    return out
+
+
+def conv_pool_fusable(h, w, cout, k):
+    return cout == 256 and k <= 128 and 2 <= w <= 64 and (w & (w - 1)) == 0 and h % 2 == 0 and 128 % (2 * w) == 0
 
 
 def conv3x3_halo(x_halo, weight, bias, *, n, h, w, cin, cout, relu=False, out=None, stats=None):

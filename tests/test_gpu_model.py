@@ -115,3 +115,50 @@ def test_c5_four_stack_variants_and_batch_sweep(J):
         with torch.no_grad():
             part = model(x[:b].cuda())[-1].cpu()
         assert torch.equal(part, full[-1][:b])
+
+
+@pytest.mark.parametrize("n,h,w,cin,res,up,x2", [(2, 64, 64, 128, True, False, 0), (3, 32, 32, 128, True, False, 0),
+                                                (5, 16, 16, 128, True, True, 0), (9, 8, 8, 64, False, False, 64),
+                                                (4, 4, 4, 128, True, False, 0), (6, 2, 2, 64, False, False, 0),
+                                                (1, 64, 64, 128, True, True, 0)])
+def test_conv1x1_fused_maxpool_output(n, h, w, cin, res, up, x2):
+    """hg_conv_desc.pool_out: the 2x2 max-pool written by the 1x1 GEMM's epilogue equals the pool kernel applied to the
+    GEMM's own (bf16) result, bit for bit, and the main result is untouched."""
+    from hgb200 import ops
+    g = torch.Generator().manual_seed(h * 7 + cin)
+    cout = 256
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).cuda()
+    k = cin + x2
+    wt = (torch.randn(cout, k, generator=g) / k ** 0.5).to(torch.bfloat16).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    r = torch.randn(n, h, w, cout, generator=g).to(torch.bfloat16).cuda() if res else None
+    lo = torch.randn(n, h // 2, w // 2, cout, generator=g).to(torch.bfloat16).cuda() if up else None
+    xx = torch.randn(n, h, w, x2, generator=g).to(torch.bfloat16).cuda() if x2 else None
+    assert ops.conv_pool_fusable(h, w, cout, k) and not ops.conv_pool_fusable(h, w, cout, 256)
+    plain = ops.conv_nhwc(x, wt, bias, ksize=1, cout=cout, residual=r, up_low=lo, x2=xx)
+    pooled = torch.full((n, h // 2, w // 2, cout), 7.0, dtype=torch.bfloat16, device="cuda")
+    fused = ops.conv_nhwc(x, wt, bias, ksize=1, cout=cout, residual=r, up_low=lo, x2=xx, pool_out=pooled)
+    torch.cuda.synchronize()
+    ops.check_err_word()
+    assert torch.equal(fused, plain)
+    assert torch.equal(pooled, ops.maxpool2x2(plain))
+
+
+def test_pool_fusion_does_not_change_the_network(monkeypatch):
+    import hgb200.engine as E
+    sd, model = _build(2, 16)
+    x = torch.randn(3, 3, 128, 128, generator=torch.Generator().manual_seed(8)).cuda()
+    outs = {}
+    for fuse in (True, False):
+        monkeypatch.setattr(E, "FUSE_POOL", fuse)
+        eng = E.HourglassEngine(sd, "cuda:0")
+        plan = eng.build_plan(3, 128, 128, use_graph=True)
+        plan.input.copy_(x)
+        plan.run()
+        torch.cuda.synchronize()
+        outs[fuse] = ([o.clone() for o in plan.outputs], plan.num_launches)
+    # three pools per stack (32^2, 16^2, 8^2 inputs: K3 of a bottleneck, K = 128) ride in their producers' epilogues, plus
+    # the first stack's 64^2 input (layer3's K3); the later 64^2 inputs come from the K = 256 remap GEMM and keep the kernel
+    assert outs[True][1] == outs[False][1] - (2 * 3 + 1)
+    for a, b in zip(outs[True][0], outs[False][0]):
+        assert torch.equal(a, b)
