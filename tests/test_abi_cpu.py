@@ -1,0 +1,53 @@
+"""The drop-in boundary on a machine without a GPU: libhgb200.so loads, exports every symbol include/hg_api.h declares
+(and the ctypes binding declares nothing else), reports the header's API version, and its argument validation answers
+with an error code + message instead of touching a device.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(REPO, "include", "hg_api.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|int64_t|size_t)\s+(hg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_library_agree():
+    from hgb200._lib import lib, lib_path, EXPORTED_SYMBOLS
+    names = declared_symbols()
+    assert len(names) >= 35 and "hg_conv_nhwc_bf16" in names and "hg_decode_final_preds_v2" in names
+    raw = C.CDLL(lib_path())
+    for n in names:
+        assert hasattr(raw, n), f"{n} is declared in include/hg_api.h but not exported by {lib_path()}"
+    assert sorted(EXPORTED_SYMBOLS) == names, (sorted(set(EXPORTED_SYMBOLS) ^ set(names)))
+    version = int(re.search(r"#define\s+HG_API_VERSION\s+(\d+)", open(HEADER).read()).group(1))
+    assert lib.hg_api_version() == version
+
+
+def test_argument_validation_needs_no_device():
+    from hgb200._lib import lib, HgError
+    assert lib.hg_conv_nhwc_bf16(None, None) != 0
+    buf = C.create_string_buffer(256)
+    assert lib.hg_last_error(buf, 256) > 0 and b"descriptor" in buf.value
+    assert lib.hg_decode_argmax(None, None, None, None, 1, 1, 4, 4, None) != 0
+    assert lib.hg_dwconv3x3_nhwc(None, None, None, None, 1, 4, 4, 64, 0, 0, None) != 0
+    assert lib.hg_preprocess_frames_u8(None, None, None, None, 1, 4, 4, 4, 4, None) != 0
+    with pytest.raises(HgError):
+        lib.check(lib.hg_wgrad_bf16(None, None, None, None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, None), "hg_wgrad_bf16")
+
+
+def test_product_path_fails_loudly_without_cuda():
+    """No CPU fallback anywhere on the product path: CPU tensors are refused (tests/test_*_cpu.py cover the models)."""
+    import torch
+    from hgb200 import ops, HgError
+    with pytest.raises(HgError):
+        ops.maxpool2x2(torch.zeros(1, 4, 4, 64, dtype=torch.bfloat16))
+    with pytest.raises(HgError):
+        ops.decode_argmax(torch.zeros(1, 1, 4, 4))
+    with pytest.raises(HgError):
+        ops.normalize_u8(torch.zeros(1, 4, 4, 3, dtype=torch.uint8), [0, 0, 0], [1, 1, 1])
