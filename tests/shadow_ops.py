@@ -18,7 +18,7 @@ PASSTHROUGH = {"halo_padded_buffer", "halo_interior", "halo_padded_elems", "gaus
 
 
 class ShadowOps:
-    def __init__(self, real_ops, bf16_tol=1.7e-2, f32_tol=2e-3):
+    def __init__(self, real_ops, bf16_tol=1.7e-2, f32_tol=5e-3):
         self.real = real_ops
         self.bf16_tol, self.f32_tol = bf16_tol, f32_tol
         self.stats = defaultdict(lambda: dict(calls=0, max_rel_l2=0.0, max_bad_frac=0.0))
@@ -55,7 +55,8 @@ class ShadowOps:
             bad = float((diff > tol * max(scale, 1e-30)).double().mean())
             st["max_rel_l2"] = max(st["max_rel_l2"], rel_l2)
             st["max_bad_frac"] = max(st["max_bad_frac"], bad)
-            if rel_l2 > tol or bad > 2e-3:
+            # (short vectors: one element on a ReLU-mask boundary is already 0.4 % of a 256-channel sum vector)
+            if rel_l2 > tol or bad > max(2e-3, 2.0 / a.numel()):
                 self.failures.append(f"{name} #{st['calls']}: shape {tuple(gpu_t.shape)} {gpu_t.dtype} rel_l2 {rel_l2:.3e} "
                                      f"bad_frac {bad:.3e}")
 
