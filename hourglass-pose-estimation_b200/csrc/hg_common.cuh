@@ -84,6 +84,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
     return r;
 }
 
+// One lane of a fully active warp (PTX elect.sync).  Branching on THIS predicate -- rather than on lane == 0 -- lets
+// ptxas treat the guarded region as single-threaded uniform code: tcgen05 / TMA operands then live in uniform registers
+// without an ELECT / BRA.U.ANY "waterfall" loop around every instruction.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // programmatic dependent launch (no-ops when the kernel was launched without the attribute)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

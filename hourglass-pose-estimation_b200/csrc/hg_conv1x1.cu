@@ -143,12 +143,12 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // broadcast: provably warp-uniform for the issue loop
     pdl_launch_dependents();     // the next kernel in the stream may begin its own setup
 
     if (warp_idx == 0) {
         // ===================== A producer: resident weights once, then the A slab stream =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             // weights / bias / bn vectors are constants: fetched BEFORE waiting on the predecessor kernel
             mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(num_kb * kBStage));
             for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem_w + kb * kBStage, &p.map_b, w_bar, kb * kBlockK, 0);
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
         }
     } else if (warp_idx == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BLOCK_N);
             bool ok = mbar_wait(w_bar, 0, p.err_word, kErrMma | 3);
             int stage = 0;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
         }
     } else if (warp_idx == 2) {
         // ===================== staging-ring producer: residual / upsample operands by TMA =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             pdl_wait();
             int buf = 0;
             uint32_t phase = 0;
@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
         pdl_wait();
         const int q = warp_idx & 3;
         const int row = q * 32 + lane;
-        const bool leader = (warp_idx == 4 && lane == 0);
+        // the slab stores are issued by ONE thread of warp 4, always the same one (elect.sync is deterministic for a given
+        // mask), because bulk async-groups are tracked per thread
         // quarter-resolution row under this pixel: tiles are 128-aligned runs of whole 2x2 blocks, so the
         // 32 low-res pixels of a tile are contiguous; row r=(y,x) within the tile maps to (y/2, x/2).
         // With W = 2^k <= 64:  r = yy*W + x  ->  low = (yy/2)*(W/2) + x/2
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                     fence_proxy_async_smem();
                     named_bar_sync(1, 128);
                 }
-                if (leader) {
+                if (warp_idx == 4 && elect_one_sync()) {
                     if (kPool) {
                         // same bulk group as the slab's own store: the read-completion wait below covers both
                         tma_store_2d(&p.map_pool, smem_pool + (pool_it & 1) * kUpBytes, slab * 64, m0 >> 2);
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
             named_bar_sync(1, 128);
             for (int i = threadIdx.x - 128; i < 2 * BLOCK_N; i += 128) atomicAdd(p.stats + i, s_stats[i]);
         }
-        if (leader) tma_store_wait<0>();
+        if (warp_idx == 4 && elect_one_sync()) tma_store_wait<0>();
     } else if (kPrologue && warp_idx >= 8) {
         // ===================== prologue: a = relu(a*scale + shift), in place =====================
         const int w = warp_idx - 8;

@@ -97,14 +97,14 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // broadcast: provably warp-uniform, so the MMA issue loop keeps it in a uniform register (no per-MMA ELECT/R2UR waterfall)
     pdl_launch_dependents();
 
     const int halo = p.P + 1;                 // positions before the tile start that the taps reach
 
     if (warp_idx == 0) {
         // ===================== A producer: one halo'd run per (tile, 64-channel slab) =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             pdl_wait();
             int it = 0;
             bool ok = true;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
         }
     } else if (warp_idx == 2) {
         // ===================== B producer: weight k-blocks (tap, slab), streamed =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
         }
     } else if (warp_idx == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;

@@ -137,14 +137,14 @@ conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // broadcast: provably warp-uniform for the issue loop
     pdl_launch_dependents();
     pdl_wait();      // everything below reads or overwrites tensors the predecessor kernel may still touch
 
     // ------------------------------------------------------------------ roles
     if (warp_idx == 0) {
         // ===================== TMA producer (one thread) =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             int stage = 0;
             uint32_t phase = 0;
             bool ok = true;
@@ -180,7 +180,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
         }
     } else if (warp_idx == 1) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
@@ -217,7 +217,6 @@ conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
         // ===================== epilogue (4 warps, one TMEM lane quarter each) =====================
         const int q = warp_idx & 3;
         const int row = q * 32 + lane;
-        const bool epi_leader = (warp_idx == 2 && lane == 0);
         const int rows_per_img = p.box_w * p.box_h;
         int it = 0;
         int slab_counter = 0;     // staging buffer ring position (continues across tiles)
@@ -285,7 +284,7 @@ conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
                 for (int slab = 0; slab < kSlabs; ++slab, ++slab_counter) {
                     uint8_t* stg = smem_stage_out + (slab_counter & 1) * kAStageBytes;
                     // the TMA store that last read this buffer (two slabs ago) must have drained
-                    if (epi_leader) tma_store_wait_read<1>();
+                    if (warp_idx == 2 && elect_one_sync()) tma_store_wait_read<1>();
                     named_bar_sync(1, kNumEpiThreads);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
@@ -353,14 +352,14 @@ conv_gemm_kernel(const __grid_constant__ ConvKernelParams p) {
                     }
                     fence_proxy_async_smem();          // generic-proxy writes -> visible to the TMA engine
                     named_bar_sync(1, kNumEpiThreads);
-                    if (epi_leader) {
+                    if (warp_idx == 2 && elect_one_sync()) {
                         tma_store_4d(&p.map_out, stg, slab * 64, x0, y0, n0);
                         tma_store_commit();
                     }
                 }
             }
         }
-        if (BLOCK_N >= 64 && epi_leader) tma_store_wait<0>();
+        if (BLOCK_N >= 64 && warp_idx == 2 && elect_one_sync()) tma_store_wait<0>();
     } else if (kPrologue) {
         // ===================== prologue: a = relu(a*scale + shift) in place (4 warps) =====================
         const int t = threadIdx.x - 192;

@@ -96,12 +96,12 @@ __global__ void __launch_bounds__(256, 1) stem_conv_kernel(const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // broadcast: provably warp-uniform for the issue loop
     pdl_launch_dependents();
     const uint32_t a_tx = static_cast<uint32_t>(p.box_w * kKb * 2);
 
     if (warp_idx == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(w_bar, kTaps * kBBlock);
             for (int kb = 0; kb < kTaps; ++kb) tma_load_2d(smem_b + kb * kBBlock, &p.map_b, w_bar, kb * kKb, 0);
             pdl_wait();
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256, 1) stem_conv_kernel(const __grid_constant
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc = umma_idesc_bf16(kTileM, kCout);
             bool ok = mbar_wait(w_bar, 0, p.err_word, 0x2203);
             int stage = 0;
@@ -159,7 +159,6 @@ __global__ void __launch_bounds__(256, 1) stem_conv_kernel(const __grid_constant
         pdl_wait();
         const int q = warp_idx & 3;
         const int row = q * 32 + lane;
-        const bool leader = (warp_idx == 4 && lane == 0);
         int it = 0;
         bool ok = true;
         for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
@@ -170,7 +169,7 @@ __global__ void __launch_bounds__(256, 1) stem_conv_kernel(const __grid_constant
             if (!ok) break;
             tc_fence_after();
             uint8_t* stg = smem_out + (it & 1) * kStaging;
-            if (leader) tma_store_wait_read<1>();
+            if (warp_idx == 4 && elect_one_sync()) tma_store_wait_read<1>();
             named_bar_sync(1, 128);
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kCout);
 #pragma unroll
@@ -198,12 +197,12 @@ __global__ void __launch_bounds__(256, 1) stem_conv_kernel(const __grid_constant
             }
             fence_proxy_async_smem();
             named_bar_sync(1, 128);
-            if (leader) {
+            if (warp_idx == 4 && elect_one_sync()) {
                 tma_store_2d(&p.map_out, stg, 0, orow * p.ow + tx * p.box_w);
                 tma_store_commit();
             }
         }
-        if (leader) tma_store_wait<0>();
+        if (warp_idx == 4 && elect_one_sync()) tma_store_wait<0>();
     }
 
     tc_fence_before();

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // broadcast: provably warp-uniform for the issue loop
     pdl_launch_dependents();
 
     const int group = blockIdx.x % p.tap_groups;           // filter row (3x3) or 0
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
     const int N = p.n_blocks * 64;
 
     if (warp_idx == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ P
             }
         }
     } else if (warp_idx == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const uint32_t idesc = umma_idesc_bf16_mn(128, N);
             int stage = 0;
             uint32_t phase = 0;
