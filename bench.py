@@ -548,6 +548,9 @@ def main():
         "config": {"workload": WORKLOAD, "images_per_gpu_per_step": B, "forwards_per_image": 2,
                    "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": "working set (>3 GB of activations per step) far exceeds the 126 MB L2; no flush needed",
+                   "note": "value (device-resident inputs) and e2e (pinned host inputs, H2D double-buffered behind compute) are "
+                           "timed in separate back-to-back regions; under sw_power_cap the SM clock drifts a few percent "
+                           "between them, so e2e can land on either side of value",
                    "weights": "random init (torch default), randomised BN statistics"},
         "tensor_tflops": flops_per_step / (ms_step * 1e-3) / 1e12,
         "tensor_frac_of_measured_peak": flops_per_step / (ms_step * 1e-3) / 1e12 / tf_sustained,
