@@ -39,7 +39,7 @@ _TEST_ALLOW_CPU = False
 _ACT = torch.bfloat16     # activation / GEMM-weight storage type (the same test switches it to fp32 for exact checks)
 # The step's launches are captured as a dependency DAG across this many CUDA streams (hgb200/dag.py);
 # 1 = one chain on one stream.
-STREAMS = int(os.environ.get("HG_TRAIN_STREAMS", "8"))
+STREAMS = int(os.environ.get("HG_TRAIN_STREAMS", "16"))
 # ... of which this many are reserved for the leaves of the DAG (weight-gradient GEMMs, bias sums) and run at normal
 # priority while the streams carrying the critical chain get CUDA's high priority (0 = no separation).
 LEAF_STREAMS = int(os.environ.get("HG_TRAIN_LEAF_STREAMS", "0"))

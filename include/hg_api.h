@@ -208,7 +208,9 @@ int hg_jmse_loss(const float* const* preds, float* const* grads, const float* ta
  * zero-initialised (or hold a partial sum): CTAs add with red.global.
  * taps == 1: off = 0.  taps == 9: both tensors are halo-padded buffers of identical geometry
  * (hg_conv3x3_halo_bf16) INCLUDING the leading zero row, rows = all positions, halo_pitch = w+1,
- * off(tap) = (tap/3-1)*halo_pitch + tap%3-1.   co <= 256 (multiple of 8), ci in {64,128,192,256}. */
+ * off(tap) = (tap/3-1)*halo_pitch + tap%3-1.   co <= 256 (multiple of 8), ci in {64,128,192,256}.
+ * The pixel range is split over at most 36 CTAs (environment variable HG_WGRAD_CTAS overrides): the kernel is meant
+ * to run beside other work of the backward pass. */
 int hg_wgrad_bf16(const void* dout, const void* z, float* dw, unsigned int* err_word, int64_t rows, int32_t co,
                   int32_t co_first, int32_t co_valid, int32_t ci, int32_t ci_valid, int32_t taps, int32_t halo_pitch, int32_t ld,
                   int32_t tap_stride, void* stream);
