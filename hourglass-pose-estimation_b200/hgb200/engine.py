@@ -27,12 +27,23 @@ from . import dag, ops
 from ._lib import HgError
 from .fold import NetWeights, BlockWeights
 
-# The forward's launches can be captured as a dependency DAG across this many CUDA streams (hgb200/dag.py) so that the
-# `up1` bottleneck of every hourglass level runs beside the lower pyramid.  Measured on B200 at batch 128 (+mirrors):
-# 5190 / 5229 / 5195 / 5172 images/s for 1 / 2 / 4 / 6 streams -- the persistent GEMM kernels own every SM, so there
-# is nothing to overlap with; the default stays one chain on one stream (the training step, whose launches are
-# small, gains 18 % from the same machinery).
-STREAMS = int(os.environ.get("HG_INFER_STREAMS", "1"))
+# The forward's launches can be captured as a dependency DAG across several CUDA streams (hgb200/dag.py) so that the
+# `up1` bottleneck of every hourglass level runs beside the lower pyramid.  Measured on B200 (images/s, flip test):
+#   batch 1: 453 -> 496 with 4 -> 8 streams;  batch 8: 2341 / 2582 / 2599 for 1 / 4 / 8 streams;  batch 32: 4365 / 4525 / 4571;
+#   batch 128: 5190 / 5229 / 5195 / 5172 for 1 / 2 / 4 / 6 streams -- there the persistent GEMM kernels own every SM and
+#   nothing is left to overlap.
+# So small batches (at most 64 rows through the network, mirrors included) use 8 streams, large ones one chain on one
+# stream; HG_INFER_STREAMS forces a count.
+_STREAMS_ENV = os.environ.get("HG_INFER_STREAMS")
+STREAMS = int(_STREAMS_ENV) if _STREAMS_ENV else 0          # 0 = choose per plan
+
+
+def streams_for(rows: int) -> int:
+    if STREAMS > 0:
+        return STREAMS
+    return 8 if rows <= 64 else 1
+
+
 # The 2x2 max-pool of a hourglass level's input is written by the epilogue of the 1x1 GEMM that produces that input
 # (hg_conv_desc.pool_out) instead of a separate kernel that re-reads it; HG_NO_POOL_FUSION=1 keeps the separate kernel.
 FUSE_POOL = os.environ.get("HG_NO_POOL_FUSION", "0") != "1"
@@ -89,6 +100,7 @@ class Plan:
         self.outputs: List[torch.Tensor] = []
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.arena_bytes = 0
+        self.streams = 1                    # CUDA streams the graph is captured across (launch DAG when > 1)
         self.heatmap = self.center = self.scale = self.coords = None
 
     @property
@@ -119,9 +131,9 @@ class Plan:
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         ops.check_err_word(self.device)
-        if STREAMS > 1:
+        if self.streams > 1:
             _, stream_of, waits = self.schedule()
-            self.graph = dag.capture(self.launches, stream_of, waits, STREAMS, self.device)
+            self.graph = dag.capture(self.launches, stream_of, waits, self.streams, self.device)
             return
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
@@ -130,7 +142,7 @@ class Plan:
 
     def schedule(self, streams: Optional[int] = None):
         """-> (dag, stream of each launch, cross-stream waits of each launch)."""
-        k = streams or STREAMS
+        k = streams or self.streams
         d = dag.build(self.records)
         cost = [4e-6 + max(m["flops"] / 6e14, m["bytes"] / 3e12) for m in self.meta]
         stream_of, waits = dag.assign_streams(d, cost, k)
@@ -207,11 +219,12 @@ class HourglassEngine:
         dev = self.device
         W = self.w
         plan = Plan(dev)
-        arena = _Arena(dev, depth=3 if (STREAMS > 1 and use_graph) else 1)
-        L = plan.launches
-        plan.input = torch.zeros((n, 3, h, w), dtype=torch.float32, device=dev)
         both = (flip == 'both')
         nb = 2 * n if both else n           # rows the network sees
+        plan.streams = streams_for(nb) if use_graph else 1
+        arena = _Arena(dev, depth=3 if plan.streams > 1 else 1)
+        L = plan.launches
+        plan.input = torch.zeros((n, 3, h, w), dtype=torch.float32, device=dev)
         halo_min_w = int(os.environ.get("HG_HALO_MIN_W", "16"))   # levels at least this wide use the halo 3x3 kernel (16x16: 28.5 vs 34.8 us)
         producer: Dict[int, int] = {}       # data_ptr of a fusable 1x1 conv's output -> index of its launch
         pool_targets: Dict[int, torch.Tensor] = {}
