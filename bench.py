@@ -302,13 +302,17 @@ def run_train(args):
     value = world * B / (ms_step * 1e-3)
     ops.check_err_word(device)
     loss1 = float(loss)
-    # ---- end to end: pinned host images + joints -> H2D, step, loss read back every step
+    # ---- end to end: pinned host images + joints -> H2D every step (on a side stream, one batch ahead), step, loss copied
+    #      back every step and read by the host one step late (hgb200/prefetch.py)
+    from hgb200.prefetch import DevicePrefetcher, LaggedScalar
+    reader = LaggedScalar(device)                                  # staging buffers are set up once, before the clock
+    feed = DevicePrefetcher(((host_x[i & 1], host_j, host_v) for i in range(steps)), device)
+    feed.preallocate((host_x[0], host_j, host_v))
     barrier()
     t0 = time.perf_counter()
-    for i in range(steps):
-        xd = host_x[i & 1].to(device, non_blocking=True)
-        jd, vd = host_j.to(device, non_blocking=True), host_v.to(device, non_blocking=True)
-        lv = float(step(xd, jd, vd).item())
+    for xd, jd, vd in feed:
+        lv = reader.push(step(xd, jd, vd))
+    lv = reader.flush()
     torch.cuda.synchronize(device)
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if world > 1:

@@ -17,6 +17,7 @@ from src.loss.mse import MSELoss
 from src import models
 from src.utils.evaluation import AverageMeter, accuracy
 from hgb200.train import train_engine, RMSPROP_ALPHA, RMSPROP_EPS
+from hgb200.prefetch import DevicePrefetcher
 
 
 def adjust_learning_rate(optimizer, epoch, lr, schedule, gamma):
@@ -157,11 +158,16 @@ class Trainer(object):
         self.model.train()
         average_loss = AverageMeter()
         average_acc = AverageMeter()
-        for i, (images, heatmaps, meta) in enumerate(self.train_loader):
-            if self.idxs:
-                heatmaps = torch.index_select(heatmaps, 1, torch.LongTensor(self.idxs))
-            loss, last_hms = self.train_step(images, heatmaps, meta['target_weight'])
-            acc = accuracy(last_hms, heatmaps.to(self.device), self.idxs, thr=self.cfg['COMMON']['pck'])
+        def host_batches():
+            for images, heatmaps, meta in self.train_loader:
+                if self.idxs:
+                    heatmaps = torch.index_select(heatmaps, 1, torch.LongTensor(self.idxs))
+                yield images, heatmaps, meta['target_weight']
+
+        # the batch of step i+1 crosses PCIe on a side stream while step i computes (hgb200/prefetch.py)
+        for images, heatmaps, target_weight in DevicePrefetcher(host_batches(), self.device):
+            loss, last_hms = self.train_step(images, heatmaps, target_weight)
+            acc = accuracy(last_hms, heatmaps, self.idxs, thr=self.cfg['COMMON']['pck'])
             average_loss.update(loss.item(), images.size(0))
             average_acc.update(acc[0], images.size(0))
         return average_loss.avg, average_acc.avg

@@ -112,3 +112,27 @@ def test_flip_test_pipeline_matches_oracle_on_its_own_heatmaps():
     assert len(outs) == 3
     for o in outs:
         np.testing.assert_array_equal(o, coords)
+
+
+def test_device_prefetcher_and_lagged_scalar():
+    """hgb200/prefetch.py: batches arrive in order and intact although the next copy is already in flight while the
+    consumer still works on the current buffers; the lagged scalar reader returns every step's value, one step late."""
+    from hgb200.prefetch import DevicePrefetcher, LaggedScalar
+    host = [(torch.full((64, 1024), float(i)).pin_memory(), torch.full((7,), i, dtype=torch.int64).pin_memory())
+            for i in range(9)]
+    reader = LaggedScalar("cuda")
+    seen, lagged = [], []
+    for i, (a, b) in enumerate(DevicePrefetcher(iter(host), "cuda")):
+        assert a.is_cuda and b.is_cuda
+        for _ in range(20):                       # keep the consumer busy on this buffer while the next copy runs
+            a = a * 1.0
+        s = (a.sum() / a.numel()) + b[0].float() * 100
+        seen.append(s)
+        v = reader.push(s)
+        if v is not None:
+            lagged.append(v)
+    lagged.append(reader.flush())
+    torch.cuda.synchronize()
+    want = [i + 100.0 * i for i in range(9)]
+    assert [float(s) for s in seen] == want
+    assert lagged == want
