@@ -48,7 +48,6 @@ class DevicePrefetcher:
         for s in range(self.depth):
             self.consumed[s].record(main)
         pending = []
-        slot = 0
         for s in range(self.depth - 1):
             if self._stage(s):
                 pending.append(s)

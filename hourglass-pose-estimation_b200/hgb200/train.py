@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import os
 from collections import defaultdict
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional
 
 import torch
 import torch.nn as nn

@@ -2,7 +2,6 @@
 quarter-pixel sign shift and inverse affine in ONE kernel launch (hg_decode_final_preds).
 `get_final_preds_v2` (inference.py:70-87, DARK-style: Gaussian blur, log, Taylor step) is hg_decode_final_preds_v2."""
 import numpy as np
-import torch
 
 from hgb200 import ops
 
