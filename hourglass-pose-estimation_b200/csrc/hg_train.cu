@@ -442,18 +442,32 @@ __global__ void __launch_bounds__(kThreads) add_inplace_kernel(uint4* dst, const
 }
 
 // ---------------------------------------------------------------- fp32 NCHW -> bf16 NHWC with channel padding
+// (heat-map gradients [n][j][h][w] -> the score convolution's dgrad / wgrad operand [n][h][w][c_pad]).  A block moves a
+// tile of 64 pixels through shared memory: reads run along the pixels of one channel plane (coalesced), writes along the
+// channels of one pixel (coalesced 16-byte chunks) -- the naive one-thread-per-element form read 4 bytes every 16 KiB.
+constexpr int kTpPix = 64;
 __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_pad_kernel(const float* __restrict__ in, __nv_bfloat16* out, int n,
                                                                      int c, int c_pad, int hw) {
     pdl_launch_dependents();
     pdl_wait();
-    const long long total = static_cast<long long>(n) * hw * c_pad;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int ch = static_cast<int>(i % c_pad);
-        const long long t = i / c_pad;
-        const int px = static_cast<int>(t % hw);
-        const long long b = t / hw;
-        out[i] = __float2bfloat16_rn(ch < c ? in[(b * c + ch) * hw + px] : 0.f);
+    __shared__ __align__(16) __nv_bfloat16 tile[kTpPix][64 + 8];        // c_pad <= 64; +8: row pitch 144 B spreads the banks
+    const int tiles_per_img = (hw + kTpPix - 1) / kTpPix;
+    const long long tiles = static_cast<long long>(n) * tiles_per_img;
+    const int px = threadIdx.x % kTpPix, cq = threadIdx.x / kTpPix;     // 4 channel lanes x 64 pixels
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const long long b = t / tiles_per_img;
+        const int p0 = static_cast<int>(t - b * tiles_per_img) * kTpPix;
+        const bool in_img = p0 + px < hw;
+        for (int ch = cq; ch < c_pad; ch += kThreads / kTpPix)
+            tile[px][ch] = __float2bfloat16_rn((ch < c && in_img) ? in[(b * c + ch) * hw + p0 + px] : 0.f);
+        __syncthreads();
+        const int chunks = c_pad / 8;                                   // 16-byte chunks per pixel
+        for (int i = threadIdx.x; i < kTpPix * chunks; i += kThreads) {
+            const int p = i / chunks, k = i - p * chunks;
+            if (p0 + p < hw)
+                *reinterpret_cast<uint4*>(out + (b * hw + p0 + p) * c_pad + k * 8) = *reinterpret_cast<const uint4*>(&tile[p][k * 8]);
+        }
+        __syncthreads();
     }
 }
 
@@ -672,12 +686,12 @@ extern "C" int hg_add_inplace_bf16(void* dst, const void* src, int64_t count, vo
 
 extern "C" int hg_nchw_f32_to_nhwc_bf16_pad(const float* in, void* out, int32_t n, int32_t c, int32_t c_pad, int32_t h,
                                             int32_t w, void* stream) {
-    if (!in || !out || n <= 0 || c <= 0 || c_pad < c || h <= 0 || w <= 0) {
-        set_last_error("hg_nchw_f32_to_nhwc_bf16_pad: bad arguments");
+    if (!in || !out || n <= 0 || c <= 0 || c_pad < c || c_pad > 64 || c_pad % 8 != 0 || h <= 0 || w <= 0 || !aligned16(out)) {
+        set_last_error("hg_nchw_f32_to_nhwc_bf16_pad: need c <= c_pad <= 64, c_pad a multiple of 8, 16-byte aligned output");
         return HG_ERR_INVALID;
     }
-    const long long items = static_cast<long long>(n) * c_pad * h * w;
-    HG_CUDA_OK(launch_kernel(nchw_to_nhwc_pad_kernel, dim3(grid_for((items + kThreads - 1) / kThreads)), dim3(kThreads), 0,
+    const long long tiles = static_cast<long long>(n) * ((static_cast<long long>(h) * w + kTpPix - 1) / kTpPix);
+    HG_CUDA_OK(launch_kernel(nchw_to_nhwc_pad_kernel, dim3(grid_for(tiles)), dim3(kThreads), 0,
                              static_cast<cudaStream_t>(stream), in, static_cast<__nv_bfloat16*>(out), n, c, c_pad, h * w));
     return HG_OK;
 }

@@ -262,7 +262,7 @@ int hg_sumpool2x2_nhwc(const void* dy, void* dlow, int32_t n, int32_t h, int32_t
 /* dst += src (bf16, fp32 add, one rounding): gradient fan-in of the residual stream. */
 int hg_add_inplace_bf16(void* dst, const void* src, int64_t count, void* stream);
 /* fp32 NCHW [n][c][h][w] -> bf16 NHWC [n][h][w][c_pad] with zero channels c..c_pad (heat-map gradients as a
- * GEMM operand). */
+ * GEMM operand).  c <= c_pad <= 64, c_pad a multiple of 8, out 16-byte aligned. */
 int hg_nchw_f32_to_nhwc_bf16_pad(const float* in, void* out, int32_t n, int32_t c, int32_t c_pad, int32_t h, int32_t w,
                                  void* stream);
 
