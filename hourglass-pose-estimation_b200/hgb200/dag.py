@@ -48,6 +48,7 @@ _WRITES: Dict[str, Tuple[Tuple, Tuple]] = {
     "add_inplace": ((0,), ()),
     "nchw_to_nhwc_bf16_pad": ((1,), ()),
     "small_gemm": ((0,), ()),
+    "pack_weights": ((), ("writes",)),          # reads / writes are passed for exactly this bookkeeping
     "jmse_loss_into": ((1, 4), ()),
     "zero_": ((0,), ()),
     "rmsprop_step": ((0, 2), ()),

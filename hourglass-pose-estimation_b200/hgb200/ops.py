@@ -570,7 +570,9 @@ def make_pack_table(entries, device) -> torch.Tensor:
     return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
 
 
-def pack_weights(table: torch.Tensor, n_entries: int):
+def pack_weights(table: torch.Tensor, n_entries: int, reads=None, writes=None):
+    """One launch that fills every bf16 GEMM weight layout from the fp32 masters (hg_pack_weights).  `reads` / `writes`
+    (lists of tensors) only tell launch recorders which buffers the table points at; the kernel takes the table."""
     _require_cuda(table)
     lib.check(lib.hg_pack_weights(_ptr(table), n_entries, _stream()), "hg_pack_weights")
 

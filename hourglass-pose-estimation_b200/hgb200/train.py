@@ -698,7 +698,11 @@ class TrainEngine:
         plan.pre.append(lambda: ops.zero_(self.stat))
         for rm in self.remap:
             plan.pre.append(lambda rm=rm: rm.merge(self.ones))
-        plan.pre.append(lambda: ops.pack_weights(self.pack_table, len(self.pack_entries)))
+        # the pack launch declares what it touches, so that launches that need no weights (input layout change, memsets)
+        # are not ordered after it in the launch DAG
+        reads = [e[k] for e in self.pack_entries for k in ("src", "src2") if e.get(k) is not None]
+        writes = [e[k] for e in self.pack_entries for k in ("dst_f32", "dst_fwd", "dst_dgrad") if e.get(k) is not None]
+        plan.pre.append(lambda: ops.pack_weights(self.pack_table, len(self.pack_entries), reads=reads, writes=writes))
 
         self._emit_backward(plan)
         for rm in self.remap:

@@ -222,7 +222,7 @@ def make_pack_table(entries, device):
     return entries
 
 
-def pack_weights(table, n_entries):
+def pack_weights(table, n_entries, reads=None, writes=None):
     for e in table:
         co, taps, ci = e["co"], e["taps"], e["ci"]
         v = e["src"][:co * taps * ci].float().clone()

@@ -66,7 +66,7 @@ class ShadowOps:
         self._tables[table.data_ptr()] = entries
         return table
 
-    def pack_weights(self, table, n_entries):
+    def pack_weights(self, table, n_entries, reads=None, writes=None):
         entries = self._tables[table.data_ptr()]
         memo = {}
         cpu_entries = self._clone_tree(entries, memo)
