@@ -473,7 +473,8 @@ __global__ void __launch_bounds__(kThreads) nchw_to_nhwc_pad_kernel(const float*
 
 // ---------------------------------------------------------------- weight packing (table-driven, one launch)
 constexpr int kPackBlocksPerEntry = 32;      // 289 -> 259 us for the 8-stack network (the transposed dgrad writes dominate)
-__global__ void __launch_bounds__(kThreads) pack_weights_kernel(const hg_pack_entry* __restrict__ table, int n_entries) {
+__global__ void __launch_bounds__(kThreads) pack_weights_kernel(const hg_pack_entry* __restrict__ table, int n_entries,
+                                                                 int which) {
     // NO early pdl_launch_dependents() here: the GEMM kernels fetch their weights BEFORE griddepcontrol.wait
     // (constants on the inference path), and a chain of small grids can run that preamble several launches ahead.
     // Without the early trigger nothing launched after this kernel starts until every packed weight is visible.
@@ -484,15 +485,19 @@ __global__ void __launch_bounds__(kThreads) pack_weights_kernel(const hg_pack_en
     const int sub = blockIdx.x - ei * kPackBlocksPerEntry;
     const int row_len = e.taps * e.ci;
     const long long total = static_cast<long long>(e.co) * row_len;
-    __nv_bfloat16* fwd = static_cast<__nv_bfloat16*>(e.dst_fwd);
-    __nv_bfloat16* dg = static_cast<__nv_bfloat16*>(e.dst_dgrad);
+    // which: bit 0 = the forward layouts (dst_fwd, dst_f32), bit 1 = the transposed dgrad layout -- two launches let the
+    // slow transposed writes run beside the forward pass, which only waits for the first
+    __nv_bfloat16* fwd = (which & 1) ? static_cast<__nv_bfloat16*>(e.dst_fwd) : nullptr;
+    float* f32 = (which & 1) ? e.dst_f32 : nullptr;
+    __nv_bfloat16* dg = (which & 2) ? static_cast<__nv_bfloat16*>(e.dst_dgrad) : nullptr;
+    if (fwd == nullptr && f32 == nullptr && dg == nullptr) return;
     for (long long idx = static_cast<long long>(sub) * kThreads + threadIdx.x; idx < total;
          idx += static_cast<long long>(kPackBlocksPerEntry) * kThreads) {
         const int o = static_cast<int>(idx / row_len);
         const int r = static_cast<int>(idx - static_cast<long long>(o) * row_len);
         float v = e.src[idx];
         if (e.src2 != nullptr) v += e.src2[idx];
-        if (e.dst_f32 != nullptr) e.dst_f32[idx] = v;
+        if (f32 != nullptr) f32[idx] = v;
         if (fwd != nullptr) fwd[static_cast<long long>(o) * e.fwd_ld + e.fwd_col0 + r] = __float2bfloat16_rn(v);
         if (dg != nullptr) {
             const int tap = r / e.ci, i = r - tap * e.ci;
@@ -696,13 +701,13 @@ extern "C" int hg_nchw_f32_to_nhwc_bf16_pad(const float* in, void* out, int32_t 
     return HG_OK;
 }
 
-extern "C" int hg_pack_weights(const hg_pack_entry* table_dev, int32_t n_entries, void* stream) {
-    if (!table_dev || n_entries <= 0) {
+extern "C" int hg_pack_weights(const hg_pack_entry* table_dev, int32_t n_entries, int32_t which, void* stream) {
+    if (!table_dev || n_entries <= 0 || which < 1 || which > 3) {
         set_last_error("hg_pack_weights: empty table");
         return HG_ERR_INVALID;
     }
     HG_CUDA_OK(launch_kernel(pack_weights_kernel, dim3(n_entries * kPackBlocksPerEntry), dim3(kThreads), 0,
-                             static_cast<cudaStream_t>(stream), table_dev, n_entries));
+                             static_cast<cudaStream_t>(stream), table_dev, n_entries, which));
     return HG_OK;
 }
 

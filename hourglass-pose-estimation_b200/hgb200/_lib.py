@@ -78,7 +78,7 @@ _SIGNATURES = {
     "hg_sumpool2x2_nhwc": ([_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_add_inplace_bf16": ([_vp, _vp, _i64, _vp], C.c_int),
     "hg_nchw_f32_to_nhwc_bf16_pad": ([_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
-    "hg_pack_weights": ([_vp, _i32, _vp], C.c_int),
+    "hg_pack_weights": ([_vp, _i32, _i32, _vp], C.c_int),
     "hg_rmsprop_step": ([_vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp], C.c_int),
     "hg_small_gemm_f32": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp], C.c_int),
     "hg_wgrad_bf16": ([_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),

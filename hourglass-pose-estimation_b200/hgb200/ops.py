@@ -570,11 +570,12 @@ def make_pack_table(entries, device) -> torch.Tensor:
     return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
 
 
-def pack_weights(table: torch.Tensor, n_entries: int, reads=None, writes=None):
+def pack_weights(table: torch.Tensor, n_entries: int, reads=None, writes=None, which: int = 3):
     """One launch that fills every bf16 GEMM weight layout from the fp32 masters (hg_pack_weights).  `reads` / `writes`
-    (lists of tensors) only tell launch recorders which buffers the table points at; the kernel takes the table."""
+    (lists of tensors) only tell launch recorders which buffers the table points at; the kernel takes the table.
+    which: 1 = forward layouts only, 2 = transposed dgrad layouts only, 3 = both."""
     _require_cuda(table)
-    lib.check(lib.hg_pack_weights(_ptr(table), n_entries, _stream()), "hg_pack_weights")
+    lib.check(lib.hg_pack_weights(_ptr(table), n_entries, int(which), _stream()), "hg_pack_weights")
 
 
 def rmsprop_step(params: torch.Tensor, grads: torch.Tensor, square_avg: torch.Tensor, lr: float, alpha: float = 0.99,

@@ -700,9 +700,13 @@ class TrainEngine:
             plan.pre.append(lambda rm=rm: rm.merge(self.ones))
         # the pack launch declares what it touches, so that launches that need no weights (input layout change, memsets)
         # are not ordered after it in the launch DAG
+        # ... and it is split in two: the forward layouts (coalesced, ~50 us), which the forward pass waits for, and the
+        # transposed dgrad layouts (scattered 2-byte writes, ~250 us), which only the backward pass needs
         reads = [e[k] for e in self.pack_entries for k in ("src", "src2") if e.get(k) is not None]
-        writes = [e[k] for e in self.pack_entries for k in ("dst_f32", "dst_fwd", "dst_dgrad") if e.get(k) is not None]
-        plan.pre.append(lambda: ops.pack_weights(self.pack_table, len(self.pack_entries), reads=reads, writes=writes))
+        w_fwd = [e[k] for e in self.pack_entries for k in ("dst_f32", "dst_fwd") if e.get(k) is not None]
+        w_dg = [e["dst_dgrad"] for e in self.pack_entries if e.get("dst_dgrad") is not None]
+        plan.pre.append(lambda: ops.pack_weights(self.pack_table, len(self.pack_entries), reads=reads, writes=w_fwd, which=1))
+        plan.pre.append(lambda: ops.pack_weights(self.pack_table, len(self.pack_entries), reads=reads, writes=w_dg, which=2))
 
         self._emit_backward(plan)
         for rm in self.remap:

@@ -33,7 +33,7 @@ extern "C" {
 #define HG_ERR_ARCH (-3)     /* device is not sm_100 */
 #define HG_ERR_DEVICE (-4)   /* a kernel reported a protocol timeout through its error word */
 
-#define HG_API_VERSION 5
+#define HG_API_VERSION 6
 
 int hg_api_version(void);
 /* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
@@ -282,7 +282,8 @@ typedef struct hg_pack_entry {
     int32_t co, taps, ci;
     int32_t fwd_ld, fwd_col0, dgrad_ld;
 } hg_pack_entry;
-int hg_pack_weights(const hg_pack_entry* table_dev, int32_t n_entries, void* stream);
+/* which: 1 = the forward layouts (dst_fwd, dst_f32), 2 = the transposed dgrad layouts, 3 = both. */
+int hg_pack_weights(const hg_pack_entry* table_dev, int32_t n_entries, int32_t which, void* stream);
 
 /* torch.optim.RMSprop step (momentum 0, centered False, weight_decay 0; trainer.py:39-41) over flat buffers:
  * g' = grad_scale*g;  v = alpha*v + (1-alpha)*g'^2;  p -= lr*g'/(sqrt(v)+eps).  count % 4 == 0. */

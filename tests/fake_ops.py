@@ -222,18 +222,18 @@ def make_pack_table(entries, device):
     return entries
 
 
-def pack_weights(table, n_entries, reads=None, writes=None):
+def pack_weights(table, n_entries, reads=None, writes=None, which=3):
     for e in table:
         co, taps, ci = e["co"], e["taps"], e["ci"]
         v = e["src"][:co * taps * ci].float().clone()
         if e.get("src2") is not None:
             v = v + e["src2"][:co * taps * ci]
-        if e.get("dst_f32") is not None:
+        if e.get("dst_f32") is not None and which & 1:
             e["dst_f32"][:co * taps * ci] = v
         w = v.view(co, taps, ci)
-        if e.get("dst_fwd") is not None:
+        if e.get("dst_fwd") is not None and which & 1:
             e["dst_fwd"][:co, e["fwd_col0"]:e["fwd_col0"] + taps * ci] = w.reshape(co, -1).to(BF)
-        if e.get("dst_dgrad") is not None:
+        if e.get("dst_dgrad") is not None and which & 2:
             e["dst_dgrad"][:, :taps * co] = w.flip(1).permute(2, 1, 0).reshape(ci, taps * co).to(BF)
 
 

@@ -66,13 +66,13 @@ class ShadowOps:
         self._tables[table.data_ptr()] = entries
         return table
 
-    def pack_weights(self, table, n_entries, reads=None, writes=None):
+    def pack_weights(self, table, n_entries, reads=None, writes=None, which=3):
         entries = self._tables[table.data_ptr()]
         memo = {}
         cpu_entries = self._clone_tree(entries, memo)
-        self.real.pack_weights(table, n_entries)
+        self.real.pack_weights(table, n_entries, which=which)
         torch.cuda.synchronize()
-        fake_ops.pack_weights(cpu_entries, n_entries)
+        fake_ops.pack_weights(cpu_entries, n_entries, which=which)
         self._compare("pack_weights", memo)
 
     def __getattr__(self, name):
