@@ -35,7 +35,7 @@ class Estimator:
         if state_dict is None:
             if not os.path.isfile(cfg['COMMON']['resume']):
                 raise FileNotFoundError('Checkpoint not found')
-            checkpoint = torch.load(cfg['COMMON']['resume'], map_location=self.device)
+            checkpoint = torch.load(cfg['COMMON']['resume'], map_location=self.device, weights_only=False)
             state_dict = checkpoint['state_dict']
         loaded_dict = OrderedDict()
         for k, v in state_dict.items():

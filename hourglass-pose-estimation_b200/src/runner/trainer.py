@@ -124,9 +124,10 @@ class Trainer(object):
 
     # ------------------------------------------------------------------ checkpoints (reference format)
     def _resume(self):
-        checkpoint = torch.load(self.cfg['COMMON']['resume'], map_location=self.device)
+        # reference checkpoints are plain pickles (numpy scalars in 'best_acc'); same trust model as the reference's torch.load
+        checkpoint = torch.load(self.cfg['COMMON']['resume'], map_location=self.device, weights_only=False)
         self.start_epoch = checkpoint['epoch']
-        self.best_acc = checkpoint['best_acc']
+        self.best_acc = float(checkpoint['best_acc'])
         sd = {(k[7:] if k.startswith('module.') else k): v for k, v in checkpoint['state_dict'].items()}
         self.model.load_state_dict(sd)
         if checkpoint.get('optimizer'):
@@ -137,7 +138,7 @@ class Trainer(object):
         return {'epoch': epoch + 1,
                 'state_dict': {'module.' + k: v.detach().clone().contiguous() for k, v in self.model.state_dict().items()},
                 'optimizer': self.optimizer.state_dict(),
-                'best_acc': self.best_acc}
+                'best_acc': float(self.best_acc)}
 
     # ------------------------------------------------------------------ one step / one epoch
     def _all_reduce(self, flat_grads):
