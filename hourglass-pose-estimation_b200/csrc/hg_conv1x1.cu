@@ -59,6 +59,7 @@ struct Params {
     int has_res, has_up, relu;
     int has_pool;           // image width when the 2x2 max-pool of the result is written too (kPool), else 0
     int out_halo, img_h, img_w;     // out_halo: map_out is the 4-D strided view (c, x, y, n) of a halo-padded buffer
+    __nv_bfloat16* out_raw;         // kRagged: the halo-padded buffer itself (rows are stored one by one, no tensor map)
 };
 
 enum : uint32_t { kErrProducer = 0x1100, kErrMma = 0x1200, kErrRing = 0x1300, kErrEpilogue = 0x1400, kErrPrologue = 0x1500 };
@@ -74,7 +75,10 @@ __device__ __forceinline__ uint32_t bf16x2_max_u32(uint32_t a, uint32_t b) {
 }
 
 // kPool: the epilogue also writes the 2x2 max-pool of its result through p.map_pool.
-template <int BLOCK_N, bool kPrologue, bool kStats, bool kPool>
+// kRagged: halo-padded output for image sizes whose 128-pixel tiles are not whole image rows (e.g. the 64x48 heat-map
+// grid of 256x192 inputs): the 4-D strided TMA store needs a rectangular box, so each epilogue thread stores its own
+// pixel's channels at the pixel's halo position instead (like the 3x3 kernel's epilogue); pads are never written.
+template <int BLOCK_N, bool kPrologue, bool kStats, bool kPool, bool kRagged = false>
 __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const __grid_constant__ Params p) {
     constexpr int kBStage = BLOCK_N * kBlockK * 2;
     constexpr int kSlabs = BLOCK_N / 64;
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&p.map_a);
         tma_prefetch_desc(&p.map_b);
-        tma_prefetch_desc(&p.map_out);
+        if (!kRagged) tma_prefetch_desc(&p.map_out);
         if (p.kb2) tma_prefetch_desc(&p.map_a2);
         if (p.has_res) tma_prefetch_desc(&p.map_res);
         if (p.has_up) tma_prefetch_desc(&p.map_up);
@@ -265,6 +269,17 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
             if (!ok) break;
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+            __nv_bfloat16* ragged_row = nullptr;       // kRagged: where this thread's pixel lives in the halo-padded buffer
+            if (kRagged) {
+                const int m = m0 + row;
+                if (m < p.m_total) {
+                    const int hw = p.img_h * p.img_w;
+                    const int n_img = m / hw, r = m - n_img * hw;
+                    const int y = r / p.img_w, x = r - y * p.img_w;
+                    const long long pos = static_cast<long long>(p.img_w + 1) * (1 + static_cast<long long>(n_img) * (p.img_h + 1) + y) + x;
+                    ragged_row = p.out_raw + pos * BLOCK_N;
+                }
+            }
             for (int slab = 0; slab < kSlabs; ++slab) {
                 ok = mbar_wait(&res_full_bar[buf], ring_phase, p.err_word, kErrEpilogue | 2);
                 if (!ok) break;
@@ -338,7 +353,11 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                             o.z = pack_bf16x2(f[i * 8 + 4], f[i * 8 + 5]);
                             o.w = pack_bf16x2(f[i * 8 + 6], f[i * 8 + 7]);
                         }
-                        sts128(stg + (((half * 4 + i) ^ (row & 7)) << 4), o);
+                        if (kRagged) {
+                            if (ragged_row != nullptr) *reinterpret_cast<uint4*>(ragged_row + col0 + i * 8) = o;
+                        } else {
+                            sts128(stg + (((half * 4 + i) ^ (row & 7)) << 4), o);
+                        }
                     }
                     if (kStats) {
                         // per-channel sum / sum of squares of what this tile produced (train-mode BatchNorm statistics
@@ -386,7 +405,10 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                     fence_proxy_async_smem();
                     named_bar_sync(1, 128);
                 }
-                if (warp_idx == 4 && elect_one_sync()) {
+                if (kRagged) {
+                    // nothing staged: the slab (at most a residual operand, read above) is free as soon as all four warps are here
+                    if (warp_idx == 4 && elect_one_sync()) mbar_arrive(&ring_empty_bar[buf]);
+                } else if (warp_idx == 4 && elect_one_sync()) {
                     if (kPool) {
                         // same bulk group as the slab's own store: the read-completion wait below covers both
                         tma_store_2d(&p.map_pool, smem_pool + (pool_it & 1) * kUpBytes, slab * 64, m0 >> 2);
@@ -405,7 +427,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                         mbar_arrive(&ring_empty_bar[prev_buf]);
                     }
                 }
-                prev_buf = buf;
+                if (!kRagged) prev_buf = buf;
                 if (kPool) ++pool_it;
                 if (++buf == p.ring) {
                     buf = 0;
@@ -509,9 +531,9 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t r
     return HG_OK;
 }
 
-template <int BLOCK_N, bool kPrologue, bool kStats, bool kPool = false>
+template <int BLOCK_N, bool kPrologue, bool kStats, bool kPool = false, bool kRagged = false>
 static int launch_variant(const Params& kp, int smem_bytes, cudaStream_t stream) {
-    auto kern = conv1x1_kernel<BLOCK_N, kPrologue, kStats, kPool>;
+    auto kern = conv1x1_kernel<BLOCK_N, kPrologue, kStats, kPool, kRagged>;
     static std::mutex mu;
     static unsigned long long done_mask = 0;
     int dev = 0;
@@ -536,6 +558,10 @@ static int launch(const Params& kp, int smem_bytes, cudaStream_t stream) {
 
 }  // namespace c1
 
+static bool halo_rectangular(const hg_conv_desc* d) {
+    return d->w <= 128 && 128 % d->w == 0 && (static_cast<long long>(d->h) * d->w) % 128 == 0;
+}
+
 // Returns 1 if this kernel can run the descriptor, 0 if the generic kernel must be used.
 int conv1x1_supported(const hg_conv_desc* d) {
     if (d->ksize != 1 || d->out_nchw_f32 != nullptr || d->out == nullptr) return 0;
@@ -544,7 +570,9 @@ int conv1x1_supported(const hg_conv_desc* d) {
     if (k > c1::kMaxK || static_cast<long long>(k) * d->cout * 2 > 128 * 1024) return 0;
     if (d->in_scale != nullptr && d->cout == 256) return 0;
     if (d->out_halo) {
-        if (d->w > 128 || 128 % d->w != 0 || (static_cast<long long>(d->h) * d->w) % 128 != 0) return 0;
+        // whole image rows per 128-pixel tile: one strided TMA store per slab; any other size: per-pixel stores (kRagged),
+        // for the 64- and 128-channel producers of the 3x3 kernel's input (w <= 253 is that kernel's own limit)
+        if (!halo_rectangular(d) && (d->cout == 256 || d->stats != nullptr || d->w > 253)) return 0;
     }
     if (d->pool_out != nullptr) {
         // the fused max-pool output: 256-channel results without prologue / statistics, whole 2x2 windows per tile
@@ -622,7 +650,11 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
     kp.out_halo = d->out_halo;
     kp.img_h = d->h;
     kp.img_w = d->w;
-    if (d->out_halo) {
+    const bool ragged = d->out_halo && !halo_rectangular(d);
+    kp.out_raw = static_cast<__nv_bfloat16*>(d->out);
+    if (ragged) {
+        // no output tensor map: see kRagged
+    } else if (d->out_halo) {
         // strided 4-D view of the interior of [zero row][n][h+1][w+1][c]
         auto enc = encode_fn();
         if (!enc) return HG_ERR_CUDA;
@@ -649,6 +681,13 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
         return launch_variant<256, false, false, true>(kp, smem_bytes, stream);
     }
 
+    if (ragged) {
+        if (d->cout == 64)
+            return prologue ? launch_variant<64, true, false, false, true>(kp, smem_bytes, stream)
+                            : launch_variant<64, false, false, false, true>(kp, smem_bytes, stream);
+        return prologue ? launch_variant<128, true, false, false, true>(kp, smem_bytes, stream)
+                        : launch_variant<128, false, false, false, true>(kp, smem_bytes, stream);
+    }
     switch (d->cout) {
         case 64: return prologue ? launch<64, true>(kp, smem_bytes, stream) : launch<64, false>(kp, smem_bytes, stream);
         case 128: return prologue ? launch<128, true>(kp, smem_bytes, stream) : launch<128, false>(kp, smem_bytes, stream);

@@ -225,6 +225,8 @@ class HourglassEngine:
         arena = _Arena(dev, depth=3 if plan.streams > 1 else 1)
         L = plan.launches
         plan.input = torch.zeros((n, 3, h, w), dtype=torch.float32, device=dev)
+        # sizes whose 128-pixel tiles are not whole image rows (64x48 maps of 256x192 inputs) store the halo layout pixel by pixel
+        ragged_halo = os.environ.get("HG_NO_RAGGED_HALO") is None
         halo_min_w = int(os.environ.get("HG_HALO_MIN_W", "16"))   # levels at least this wide use the halo 3x3 kernel (16x16: 28.5 vs 34.8 us)
         producer: Dict[int, int] = {}       # data_ptr of a fusable 1x1 conv's output -> index of its launch
         pool_targets: Dict[int, torch.Tensor] = {}
@@ -269,8 +271,8 @@ class HourglassEngine:
                                       flops=2.0 * bn_ * bh_ * bw_ * 9 * bw.planes, bytes=a2.numel() * 4))
                 L.append(lambda: ops.dwconv3x3(a2, bw.w2, bw.b2, relu=True, out=a3))
                 arena.put(a2)
-            elif (bw_ >= halo_min_w and bw_ <= 128 and 128 % bw_ == 0 and (bh_ * bw_) % 128 == 0
-                    and bw.planes in (64, 128) and x.shape[3] <= 512):
+            elif (bw_ >= halo_min_w and bw_ <= 253 and bw.planes in (64, 128) and x.shape[3] <= 512
+                    and (ragged_halo or (bw_ <= 128 and 128 % bw_ == 0 and (bh_ * bw_) % 128 == 0))):
                 # K1 writes the halo-padded layout; K2 reads every input pixel once (hg_conv3x3.cu)
                 a2h = arena.get_halo(bn_, bh_, bw_, bw.planes)
                 pixels = bn_ * bh_ * bw_

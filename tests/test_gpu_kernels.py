@@ -42,6 +42,50 @@ def test_conv_gemm(case, ops, dev):
     assert err <= tol, f"{case[0]}: max abs err {err} > {tol} (scale {scale})"
 
 
+def _fuzz_cases(count, seed):
+    import random
+    rnd = random.Random(seed)
+    cases = []
+    for i in range(count):
+        ksize = rnd.choice([1, 1, 3])
+        heads = ksize == 1 and rnd.random() < 0.15
+        cin = rnd.choice([64, 128, 256]) if not heads else 256
+        cout = rnd.randint(1, 32) if heads else rnd.choice([32, 64, 128, 256] if ksize == 1 else [64, 128])
+        if ksize == 3:
+            cin = cout
+        up = (not heads) and ksize == 1 and rnd.random() < 0.3
+        h, w = rnd.randint(1, 20), rnd.randint(1, 20)
+        if up or rnd.random() < 0.5:
+            h, w = 2 * h, 2 * w
+        n = rnd.randint(1, 7)
+        residual = up or ((not heads) and rnd.random() < 0.4)
+        prologue = ksize == 1 and not heads and rnd.random() < 0.4
+        cin2 = rnd.choice([0, 0, 64, 128]) if (ksize == 1 and not heads and not prologue) else 0
+        cases.append((f"fuzz{i}", n, h, w, cin, cout, ksize, rnd.random() < 0.5, prologue, residual, up, cin2, heads))
+    return cases
+
+
+def test_conv_fuzz_random_shapes(ops, dev):
+    """Seeded random shapes (ragged tiles, odd sizes, 1-pixel images, every epilogue combination): a case either
+    matches the fp32 reference or is REJECTED with an HgError -- never a wrong answer, a hang or a sticky error."""
+    from hgb200 import HgError
+    ran, rejected = 0, []
+    for case in _fuzz_cases(72, seed=11):
+        t = make_conv_case(case, dev)
+        try:
+            out = run_conv_case(t)
+        except (HgError, ValueError) as e:
+            rejected.append((case, str(e)[:80]))
+            continue
+        ref = conv_reference(t)
+        scale = float(ref.abs().max())
+        tol = scale * (1e-3 if t["heads"] else 2 ** -7)
+        err = float((out - ref).abs().max())
+        assert torch.isfinite(out).all() and err <= tol, f"{case}: max abs err {err} > {tol}"
+        ran += 1
+    assert ran >= 48, f"only {ran} cases ran; rejected: {rejected}"
+
+
 def test_conv_rejects_bad_shapes(ops, dev):
     from hgb200 import HgError
     x = torch.zeros(1, 8, 8, 48, dtype=torch.bfloat16, device=dev)
@@ -111,6 +155,49 @@ def test_conv1x1_writes_halo_padded_output(shape, ops, dev):
     full = buf[(w + 1) * cout:].view(n, h + 1, w + 1, cout)
     assert float(full[:, h].abs().max()) == 0 and float(full[:, :, w].abs().max()) == 0      # pads untouched
     assert float(buf[:(w + 1) * cout].abs().max()) == 0
+
+
+def test_halo_chain_fuzz_random_shapes(ops, dev):
+    """1x1 (+bn prologue) -> halo-padded buffer -> 3x3 on seeded random shapes (odd widths, 1-row images, widths up
+    to the kernel's limit): bit-identical to the dense 1x1 followed by the generic 3x3 path's operands, and within one
+    bf16 rounding of the fp32 reference."""
+    import random
+    from hgb200 import HgError
+    no_tf32()
+    rnd = random.Random(5)
+    ran = 0
+    for i in range(40):
+        n, h = rnd.randint(1, 6), rnd.randint(1, 40)
+        w = rnd.choice([1, 2, 3, 5, 8, 17, 31, 48, 64, 100, 253]) if i % 4 == 0 else rnd.randint(1, 72)
+        cin, c = rnd.choice([64, 128, 256]), rnd.choice([64, 128])
+        if w > 100:
+            n, h = 1, rnd.randint(1, 6)
+        g = torch.Generator().manual_seed(100 + i)
+        x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).to(dev)
+        w1 = (torch.randn(c, cin, generator=g) / cin ** 0.5).to(torch.bfloat16).to(dev)
+        b1 = (torch.randn(c, generator=g) * 0.5).to(dev)
+        w3 = torch.randn(c, c, 3, 3, generator=g) / (3.0 * c ** 0.5)
+        b3 = (torch.randn(c, generator=g) * 0.5).to(dev)
+        scale = (0.5 + torch.rand(cin, generator=g)).to(dev)
+        shift = (0.3 * torch.randn(cin, generator=g)).to(dev)
+        try:
+            dense = ops.conv_nhwc(x, w1, b1, ksize=1, cout=c, relu=True, in_scale=scale, in_shift=shift)
+            buf = ops.halo_padded_buffer(n, h, w, c, dev)
+            ops.conv_nhwc(x, w1, b1, ksize=1, cout=c, relu=True, in_scale=scale, in_shift=shift, out_halo=buf)
+            wmat = w3.permute(0, 2, 3, 1).reshape(c, 9 * c).to(torch.bfloat16).to(dev)
+            out = ops.conv3x3_halo(buf, wmat, b3, n=n, h=h, w=w, cin=c, cout=c, relu=bool(i & 1))
+        except (HgError, ValueError):
+            continue
+        torch.cuda.synchronize()
+        ops.check_err_word(dev)
+        assert torch.equal(ops.halo_interior(buf, n, h, w, c), dense), (n, h, w, cin, c)
+        ref = F.conv2d(dense.float().permute(0, 3, 1, 2), r16(w3).to(dev), b3, padding=1)
+        if i & 1:
+            ref = F.relu(ref)
+        err = float((out.float().permute(0, 3, 1, 2) - ref).abs().max())
+        assert err <= float(ref.abs().max()) * 2 ** -7, f"{(n, h, w, cin, c)}: err {err} vs scale {float(ref.abs().max())}"
+        ran += 1
+    assert ran >= 30, ran
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 96), (1, 256, 256), (2, 256, 192), (3, 128, 512)])
