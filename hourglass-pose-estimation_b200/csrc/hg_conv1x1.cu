@@ -60,7 +60,17 @@ struct Params {
     int has_pool;           // image width when the 2x2 max-pool of the result is written too (kPool), else 0
     int out_halo, img_h, img_w;     // out_halo: map_out is the 4-D strided view (c, x, y, n) of a halo-padded buffer
     __nv_bfloat16* out_raw;         // kRagged: the halo-padded buffer itself (rows are stored one by one, no tensor map)
+    // Row tiling (tiles_per_img != 0): a tile is `tile_pixels` = R whole image rows (R*w <= 128) of ONE image instead of 128
+    // consecutive pixels, so that the geometric epilogues (halo / 4-D store, upsample operand) work for any width <= 128;
+    // the rest of the 128-row MMA tile computes on stale shared memory and is clipped by the 4-D TMA store.
+    int tile_pixels, tiles_per_img, img_hw;
 };
+
+__device__ __forceinline__ int tile_m0(const Params& p, int tile) {
+    if (p.tiles_per_img == 0) return tile * kTileM;
+    const int img = tile / p.tiles_per_img;
+    return img * p.img_hw + (tile - img * p.tiles_per_img) * p.tile_pixels;
+}
 
 enum : uint32_t { kErrProducer = 0x1100, kErrMma = 0x1200, kErrRing = 0x1300, kErrEpilogue = 0x1400, kErrPrologue = 0x1500 };
 
@@ -161,11 +171,11 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
             uint32_t phase = 0;
             bool ok = true;
             for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
-                const int m0 = tile * kTileM;
+                const int m0 = tile_m0(p, tile);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     ok = mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_word, kErrProducer | 1);
                     if (!ok) break;
-                    mbar_arrive_expect_tx(&full_bar[stage], kSlabBytes);
+                    mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(p.tile_pixels * 128));
                     if (kb < p.kb1)
                         tma_load_2d(smem_a + stage * kSlabBytes, &p.map_a, &full_bar[stage], kb * kBlockK, m0);
                     else
@@ -217,9 +227,9 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
             int buf = 0;
             uint32_t phase = 0;
             bool ok = true;
-            const uint32_t tx = static_cast<uint32_t>((p.has_res ? kSlabBytes : 0) + (p.has_up ? kUpBytes : 0));
+            const uint32_t tx = static_cast<uint32_t>((p.has_res ? p.tile_pixels * 128 : 0) + (p.has_up ? p.tile_pixels * 32 : 0));
             for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x) {
-                const int m0 = tile * kTileM;
+                const int m0 = tile_m0(p, tile);
                 for (int slab = 0; slab < kSlabs; ++slab) {
                     ok = mbar_wait(&ring_empty_bar[buf], phase ^ 1u, p.err_word, kErrRing | 1);
                     if (!ok) break;
@@ -264,7 +274,7 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
         for (int tile = blockIdx.x; tile < p.num_tiles && ok; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1u;
-            const int m0 = tile * kTileM;
+            const int m0 = tile_m0(p, tile);
             ok = mbar_wait(&tmem_full_bar[acc], acc_phase, p.err_word, kErrEpilogue | 1);
             if (!ok) break;
             tc_fence_after();
@@ -562,6 +572,40 @@ static bool halo_rectangular(const hg_conv_desc* d) {
     return d->w <= 128 && 128 % d->w == 0 && (static_cast<long long>(d->h) * d->w) % 128 == 0;
 }
 
+// the TMA-fed upsample operand of a flat tile (128 consecutive pixels) needs whole 2x2 blocks inside every tile
+static bool flat_upsample_ok(const hg_conv_desc* d) {
+    const int w = d->w, h = d->h;
+    const bool pow2 = (w & (w - 1)) == 0;
+    return pow2 && w <= 64 && w >= 2 && !(h & 1) && 128 % (2 * w) == 0;
+}
+
+// Image rows per tile when tiles are whole rows of one image (Params::tiles_per_img), 0 if the size does not allow it.
+static int row_tile_rows(const hg_conv_desc* d) {
+    static const bool off = getenv("HG_CONV1X1_NO_ROWTILE") != nullptr;
+    if (off || d->w > 128 || d->w < 1) return 0;
+    int r = 128 / d->w;
+    if (r > d->h) r = d->h;
+    if (d->up_low != nullptr) {
+        if ((d->h | d->w) & 1) return 0;
+        r &= ~1;
+    }
+    return r;
+}
+
+enum { kGeomFlat = 0, kGeomRows = 1, kGeomRagged = 2, kGeomNone = -1 };
+
+// How the tile -> pixel mapping is chosen for the epilogues that depend on image geometry (halo output, upsample operand).
+static int geometry_mode(const hg_conv_desc* d) {
+    const bool flat_ok = (!d->out_halo || halo_rectangular(d)) && (d->up_low == nullptr || flat_upsample_ok(d));
+    if (flat_ok) return kGeomFlat;
+    if (row_tile_rows(d) > 0 && d->stats == nullptr && d->pool_out == nullptr) return kGeomRows;
+    // per-pixel stores of the halo layout: the 64- and 128-channel producers of the 3x3 kernel's input (w <= 253 is that
+    // kernel's own limit)
+    if (d->out_halo && d->up_low == nullptr && d->cout != 256 && d->stats == nullptr && d->pool_out == nullptr && d->w <= 253)
+        return kGeomRagged;
+    return kGeomNone;
+}
+
 // Returns 1 if this kernel can run the descriptor, 0 if the generic kernel must be used.
 int conv1x1_supported(const hg_conv_desc* d) {
     if (d->ksize != 1 || d->out_nchw_f32 != nullptr || d->out == nullptr) return 0;
@@ -569,11 +613,7 @@ int conv1x1_supported(const hg_conv_desc* d) {
     const int k = d->cin + d->cin2;
     if (k > c1::kMaxK || static_cast<long long>(k) * d->cout * 2 > 128 * 1024) return 0;
     if (d->in_scale != nullptr && d->cout == 256) return 0;
-    if (d->out_halo) {
-        // whole image rows per 128-pixel tile: one strided TMA store per slab; any other size: per-pixel stores (kRagged),
-        // for the 64- and 128-channel producers of the 3x3 kernel's input (w <= 253 is that kernel's own limit)
-        if (!halo_rectangular(d) && (d->cout == 256 || d->stats != nullptr || d->w > 253)) return 0;
-    }
+    if (geometry_mode(d) == kGeomNone) return 0;
     if (d->pool_out != nullptr) {
         // the fused max-pool output: 256-channel results without prologue / statistics, whole 2x2 windows per tile
         const int w = d->w, h = d->h;
@@ -583,13 +623,6 @@ int conv1x1_supported(const hg_conv_desc* d) {
         // shrinking the staging ring, and the kernel loses more than the pool pass costs (measured: 481 vs 284 + 110 us)
         if (d->cin + d->cin2 > 128) return 0;
         if (!pow2 || w > 64 || w < 2 || (h & 1) || 128 % (2 * w) != 0) return 0;
-    }
-    if (d->up_low != nullptr) {
-        // the TMA-fed upsample operand needs whole 2x2 blocks inside every 128-pixel tile
-        const int w = d->w, h = d->h;
-        const bool pow2 = (w & (w - 1)) == 0;
-        if (!pow2 || w > 64 || w < 2 || (h & 1)) return 0;
-        if (128 % (2 * w) != 0) return 0;
     }
     return 1;
 }
@@ -611,6 +644,16 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
     kp.stats = d->stats;
     kp.m_total = static_cast<int>(m);
     kp.num_tiles = static_cast<int>((m + kTileM - 1) / kTileM);
+    const int geom = geometry_mode(d);
+    const int tile_rows = geom == kGeomRows ? row_tile_rows(d) : 0;
+    kp.tile_pixels = kTileM;
+    kp.img_hw = d->h * d->w;
+    if (geom == kGeomRows) {
+        kp.tile_pixels = tile_rows * d->w;
+        kp.tiles_per_img = (d->h + tile_rows - 1) / tile_rows;
+        kp.num_tiles = d->n * kp.tiles_per_img;
+    }
+    const uint32_t box_m = static_cast<uint32_t>(kp.tile_pixels);
     kp.kb1 = d->cin / 64;
     kp.kb2 = d->cin2 / 64;
     kp.cin = d->cin;
@@ -644,26 +687,29 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
     const int smem_bytes = 1024 + wbytes + a_stages * kSlabBytes + ring * ring_unit + misc;
 
     int rc;
-    if ((rc = make_map(&kp.map_a, d->in, d->cin, m, kTileM)) != HG_OK) return rc;
-    if (d->in2 && (rc = make_map(&kp.map_a2, d->in2, d->cin2, m, kTileM)) != HG_OK) return rc;
+    if ((rc = make_map(&kp.map_a, d->in, d->cin, m, box_m)) != HG_OK) return rc;
+    if (d->in2 && (rc = make_map(&kp.map_a2, d->in2, d->cin2, m, box_m)) != HG_OK) return rc;
     if ((rc = make_map(&kp.map_b, d->weight, d->cin + d->cin2, d->cout, d->cout)) != HG_OK) return rc;
     kp.out_halo = d->out_halo;
     kp.img_h = d->h;
     kp.img_w = d->w;
-    const bool ragged = d->out_halo && !halo_rectangular(d);
+    const bool ragged = geom == kGeomRagged;
     kp.out_raw = static_cast<__nv_bfloat16*>(d->out);
     if (ragged) {
         // no output tensor map: see kRagged
-    } else if (d->out_halo) {
-        // strided 4-D view of the interior of [zero row][n][h+1][w+1][c]
+    } else if (d->out_halo || geom == kGeomRows) {
+        // 4-D view (c, x, y, n): the interior of the halo-padded [zero row][n][h+1][w+1][c], or (row tiling) the dense NHWC
+        // tensor -- there the 4-D box is what clips the last, partial tile of every image
         auto enc = encode_fn();
         if (!enc) return HG_ERR_CUDA;
-        const uint64_t C = d->cout, P = d->w + 1;
+        const uint64_t C = d->cout, P = d->out_halo ? d->w + 1 : d->w, HP = d->out_halo ? d->h + 1 : d->h;
+        const uint32_t box_rows = geom == kGeomRows ? static_cast<uint32_t>(tile_rows) : static_cast<uint32_t>(kTileM / d->w);
         cuuint64_t gdim[4] = {C, static_cast<cuuint64_t>(d->w), static_cast<cuuint64_t>(d->h), static_cast<cuuint64_t>(d->n)};
-        cuuint64_t gstr[3] = {C * 2, P * C * 2, static_cast<cuuint64_t>(d->h + 1) * P * C * 2};
-        cuuint32_t box[4] = {64, static_cast<cuuint32_t>(d->w), static_cast<cuuint32_t>(kTileM / d->w), 1};
+        cuuint64_t gstr[3] = {C * 2, P * C * 2, HP * P * C * 2};
+        cuuint32_t box[4] = {64, static_cast<cuuint32_t>(d->w), box_rows, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        void* base = static_cast<char*>(d->out) + P * C * 2;        // skip the leading zero row
+        void* base = static_cast<char*>(d->out) + (d->out_halo ? P * C * 2 : 0);        // skip the leading zero row
+        kp.out_halo = 1;                                                               // = "store through the 4-D map"
         CUresult r = enc(&kp.map_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -674,8 +720,8 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
     } else if ((rc = make_map(&kp.map_out, d->out, d->cout, m, kTileM)) != HG_OK) {
         return rc;
     }
-    if (d->residual && (rc = make_map(&kp.map_res, d->residual, d->cout, m, kTileM)) != HG_OK) return rc;
-    if (d->up_low && (rc = make_map(&kp.map_up, d->up_low, d->cout, m / 4, kUpRows)) != HG_OK) return rc;
+    if (d->residual && (rc = make_map(&kp.map_res, d->residual, d->cout, m, box_m)) != HG_OK) return rc;
+    if (d->up_low && (rc = make_map(&kp.map_up, d->up_low, d->cout, m / 4, box_m / 4)) != HG_OK) return rc;
     if (d->pool_out) {
         if ((rc = make_map(&kp.map_pool, d->pool_out, d->cout, m / 4, kUpRows)) != HG_OK) return rc;
         return launch_variant<256, false, false, true>(kp, smem_bytes, stream);

@@ -50,6 +50,10 @@ CONV_CASES = [
     ("1x1_up_4x4", 9, 4, 4, 128, 256, 1, False, False, True, True, 0, False),
     ("1x1_up_64x48_generic", 2, 64, 48, 128, 256, 1, False, False, True, True, 0, False),
     ("1x1_up_6x6_generic", 3, 6, 6, 128, 256, 1, False, False, True, True, 0, False),
+    ("1x1_up_22x24_rows", 3, 22, 24, 128, 256, 1, False, False, True, True, 0, False),
+    ("1x1_up_64x96_wide", 1, 64, 96, 128, 256, 1, False, False, True, True, 0, False),
+    ("1x1_up_10x12_relu_rows", 5, 10, 12, 256, 256, 1, True, False, True, True, 0, False),
+    ("1x1_up_2x2", 5, 2, 2, 128, 256, 1, False, False, True, True, 0, False),
     ("1x1_ragged_res_n256", 3, 10, 6, 128, 256, 1, False, False, True, False, 0, False),
     ("1x1_two_inputs_n256", 2, 32, 32, 128, 256, 1, False, False, False, False, 128, False),
     ("1x1_remap_relu", 2, 64, 64, 256, 256, 1, True, False, True, False, 0, False),
