@@ -11,6 +11,9 @@ python bench.py --workload train --steps 10 --warmup 3 --breakdown gpurun_out/tr
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r1.json 2>&1; echo "ref exit $?"
 # stock PyTorch (cuDNN) on the same GPU: the reference network as plain torch ops, fp32 / TF32 / bf16 channels_last
 python tests/gpu_stock_torch_baseline.py gpurun_out/stock_torch_b200.json > gpurun_out/stock_torch.log 2>&1; echo "stock torch exit $?"
+# the COCO-shaped configuration (C4: 256x192, J=17): inference forward and training step with per-class breakdowns
+python tools/c4_time.py --breakdown > gpurun_out/c4_infer_r1.log 2>&1; echo "c4 infer exit $?"
+python tools/c4_train_time.py > gpurun_out/c4_train_r1.log 2>&1; echo "c4 train exit $?"
 # launch list of ONE pass of the inference step (the eager warm-up pass: same kernels as a graph replay)
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -s 0 -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list_r1.log 2>&1; echo "ncu list exit $?"
 # launch list of the training step's eager recording pass (everything from pack_weights on)
