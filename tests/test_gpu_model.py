@@ -117,6 +117,31 @@ def test_c5_four_stack_variants_and_batch_sweep(J):
         assert torch.equal(part, full[-1][:b])
 
 
+def test_maximum_batch_crosses_the_32_bit_element_limit():
+    """Maximum sizes: 2112 rows at 64x64x256 channels are 2.2 G elements / 4.4 GB per activation tensor -- past both 2^31
+    elements and 2^32 bytes, so any 32-bit index arithmetic in a kernel shows up.  No oracle can run this batch; the
+    check is the size-independent property of the path: an image's heat maps do not depend on its batch (bit-identical
+    to the same image in a batch of three), checked at the start, the middle and the far end of the large batch."""
+    sd, model = _build(1, 16, seed=5)
+    g = torch.Generator().manual_seed(6)
+    x3 = torch.randn(3, 3, 256, 256, generator=g)
+    n = 2112
+    with torch.no_grad():
+        small = model(x3.cuda())[-1]
+        big_in = x3.repeat(n // 3, 1, 1, 1).cuda()
+        big = model(big_in)[-1]
+    torch.cuda.synchronize()
+    from hgb200 import ops
+    ops.check_err_word(torch.device("cuda:0"))
+    assert big.shape == (n, 16, 64, 64)
+    for start in (0, 1056, n - 3):
+        assert torch.equal(big[start:start + 3], small), start
+    assert torch.equal(big.view(n // 3, 3, 16, 64, 64)[::37], small.expand(len(range(0, n // 3, 37)), -1, -1, -1, -1))
+    del big, big_in
+    model._engine = None
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("n,h,w,cin,res,up,x2", [(2, 64, 64, 128, True, False, 0), (3, 32, 32, 128, True, False, 0),
                                                 (5, 16, 16, 128, True, True, 0), (9, 8, 8, 64, False, False, 64),
                                                 (4, 4, 4, 128, True, False, 0), (6, 2, 2, 64, False, False, 0),
