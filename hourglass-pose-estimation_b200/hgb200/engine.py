@@ -428,6 +428,9 @@ class HourglassEngine:
         if x.dim() != 4 or x.shape[1] != 3:
             raise HgError(f"expected [n,3,h,w], got {tuple(x.shape)}")
         n, _, h, w = x.shape
+        if n == 0:      # an empty batch gives empty heat maps, as the reference's modules do
+            return [torch.zeros((0, self.num_classes, h // 4, w // 4), dtype=torch.float32, device=self.device)
+                    for _ in range(self.num_stacks)]
         plan = self.plan_for(n, h, w, flip, use_graph)
         plan.input.copy_(x, non_blocking=True)
         plan.run()

@@ -16,6 +16,9 @@ def get_preds(batch_heatmaps):
         Output: coords of joint [batch, njoint, 2]   (float32, on the heat maps' device)
     """
     assert batch_heatmaps.dim() == 4, 'Score maps should be 4-dim'
+    if batch_heatmaps.shape[0] == 0 or batch_heatmaps.shape[1] == 0:     # torch.max over an empty batch: empty result
+        return torch.zeros(batch_heatmaps.shape[0], batch_heatmaps.shape[1], 2, dtype=torch.float32,
+                           device=batch_heatmaps.device)
     preds, _, _ = ops.decode_argmax(batch_heatmaps)
     return preds if batch_heatmaps.is_cuda else preds.cpu()
 

@@ -117,6 +117,16 @@ def test_c5_four_stack_variants_and_batch_sweep(J):
         assert torch.equal(part, full[-1][:b])
 
 
+def test_empty_batch_gives_empty_heatmaps():
+    """Empty input (reference: every torch module passes a 0-sized batch through): a list of S empty heat maps, empty coords."""
+    from src.utils.evaluation import get_preds
+    _, model = _build(2, 16, seed=1)
+    with torch.no_grad():
+        out = model(torch.zeros(0, 3, 256, 192, device="cuda"))
+    assert len(out) == 2 and all(o.shape == (0, 16, 64, 48) and o.dtype == torch.float32 and o.is_cuda for o in out)
+    assert get_preds(out[-1]).shape == (0, 16, 2)
+
+
 def test_maximum_batch_crosses_the_32_bit_element_limit():
     """Maximum sizes: 2112 rows at 64x64x256 channels are 2.2 G elements / 4.4 GB per activation tensor -- past both 2^31
     elements and 2^32 bytes, so any 32-bit index arithmetic in a kernel shows up.  No oracle can run this batch; the
