@@ -292,6 +292,252 @@ __global__ void __launch_bounds__(256, 1) conv3x3_kernel(const __grid_constant__
     }
 }
 
+// ================================================================================================================
+// Paired-CTA variant (cta_group::2): the two CTAs of a cluster share ONE 256-position tile.  Each CTA stages the
+// halo'd run of its own 128 positions and HALF of every weight k-block (64 of the 128 output channels' rows); the
+// leader CTA issues M=256 MMAs that read A and B from both CTAs' shared memory and write each CTA's 128 accumulator
+// rows into that CTA's TMEM.  Per CTA this halves the shared memory of the single-CTA kernel (2 x 34 KB of A regions,
+// 8 KB weight stages) and its TMEM (2 x 128 columns) at the same weight traffic per position -- the room the K2+K3
+// fusion needs.  Selected with HG_CONV3X3_PAIR=1 (cout = 128, no statistics).
+// ================================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-SM TMA load: lands in THIS CTA's shared memory, completes its bytes on the LEADER CTA's mbarrier (same offset, peer bit
+// cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// one arrival on the barrier at this offset in BOTH CTAs once every MMA issued so far has retired
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_leader(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
+
+constexpr int kPairBStages = 16;
+constexpr int kPairBStage = 64 * kBlockK * 2;          // this CTA's half of a [128 x 64] weight k-block
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv3x3_pair_kernel(const __grid_constant__ Params p) {
+    constexpr int BLOCK_N = 128;
+    constexpr int kTmemCols = 2 * BLOCK_N;              // 2 accumulator stages of this CTA's 128 rows
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                    // 2 regions
+    uint8_t* smem_b = smem_a + 2 * p.region_bytes;             // b_stages x 8 KiB
+    float* s_bias = reinterpret_cast<float*>(smem_b + p.b_stages * kPairBStage);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
+    uint64_t* a_full = bars;                  // [2]   (used in the leader)
+    uint64_t* a_empty = bars + 2;             // [2]
+    uint64_t* b_full = bars + 4;              // [kPairBStages] (used in the leader)
+    uint64_t* b_empty = b_full + kPairBStages;
+    uint64_t* tmem_full_bar = b_empty + kPairBStages;   // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]   (used in the leader: 4 epilogue warps of each CTA)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&p.map_a);
+        tma_prefetch_desc(&p.map_b);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+            mbar_init(&tmem_full_bar[s], 1);
+            mbar_init(&tmem_empty_bar[s], 8);
+        }
+        for (int s = 0; s < kPairBStages; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp_idx == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                        // both CTAs' barriers exist before either one's TMA / commit can touch them
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+    pdl_launch_dependents();
+
+    const int halo = p.P + 1;
+
+    if (warp_idx == 0) {
+        // ===================== A producer: this CTA's 128 positions (+ halo) per (tile, slab) =====================
+        if (elect_one_sync()) {
+            pdl_wait();
+            int it = 0;
+            bool ok = true;
+            for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs) {
+                const long long f0 = static_cast<long long>(p.P) + static_cast<long long>(tile) * kBM + rank * 128;
+                const int row0 = static_cast<int>(f0 - halo);
+                for (int slab = 0; slab < p.slabs; ++slab, ++it) {
+                    const int buf = it & 1;
+                    ok = mbar_wait(&a_empty[buf], ((it >> 1) & 1u) ^ 1u, p.err_word, 0x3501);
+                    if (!ok) break;
+                    if (leader) mbar_arrive_expect_tx(&a_full[buf], static_cast<uint32_t>(2 * p.num_boxes * p.box_rows * 128));
+                    for (int b = 0; b < p.num_boxes; ++b)
+                        tma_load_2d_2sm(smem_a + buf * p.region_bytes + b * p.box_rows * 128, &p.map_a, &a_full[buf],
+                                        slab * kBlockK, row0 + b * p.box_rows);
+                }
+            }
+        }
+    } else if (warp_idx == 2) {
+        // ===================== B producer: this CTA's 64 output-channel rows of every k-block =====================
+        if (elect_one_sync()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs) {
+                for (int slab = 0; slab < p.slabs && ok; ++slab) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ok = mbar_wait(&b_empty[stage], phase ^ 1u, p.err_word, 0x3701);
+                        if (!ok) break;
+                        if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * kPairBStage);
+                        tma_load_2d_2sm(smem_b + stage * kPairBStage, &p.map_b, &b_full[stage], tap * p.cin + slab * kBlockK,
+                                        static_cast<int>(rank) * 64);
+                        if (++stage == p.b_stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && elect_one_sync()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(256, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0, a_it = 0;
+            bool ok = true;
+            for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs, ++it) {
+                const int acc = it & 1;
+                ok = mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1u) ^ 1u, p.err_word, 0x3601);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+                for (int slab = 0; slab < p.slabs && ok; ++slab, ++a_it) {
+                    const int buf = a_it & 1;
+                    ok = mbar_wait(&a_full[buf], (a_it >> 1) & 1u, p.err_word, 0x3602);
+                    if (!ok) break;
+                    const uint32_t a_base = smem_u32(smem_a + buf * p.region_bytes);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ok = mbar_wait(&b_full[stage], phase, p.err_word, 0x3603);
+                        if (!ok) break;
+                        tc_fence_after();
+                        const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                        const uint32_t row_off = static_cast<uint32_t>(halo + dy * p.P + dx);
+                        const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + stage * kPairBStage));
+                        const uint64_t a_desc = umma_desc_sw128(a_base + row_off * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_bf16_2sm(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (slab | tap | k) != 0 ? 1u : 0u);
+                        tc_commit_2sm(&b_empty[stage]);
+                        if (++stage == p.b_stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    if (ok) tc_commit_2sm(&a_empty[buf]);
+                }
+                if (ok) tc_commit_2sm(&tmem_full_bar[acc]);
+            }
+        }
+    } else if (warp_idx >= 4) {
+        // ===================== epilogue: this CTA's 128 rows =====================
+        pdl_wait();
+        const int q = warp_idx & 3;
+        const int row = q * 32 + lane;
+        const long long img_pos = static_cast<long long>(p.H + 1) * p.P;
+        int it = 0;
+        bool ok = true;
+        for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs, ++it) {
+            const int acc = it & 1;
+            ok = mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1u, p.err_word, 0x3801);
+            if (!ok) break;
+            tc_fence_after();
+            const long long f = static_cast<long long>(tile) * kBM + rank * 128 + row;
+            const long long n = f / img_pos;
+            const int r = static_cast<int>(f - n * img_pos);
+            const int y = r / p.P, x = r - y * p.P;
+            const bool valid = (f < p.total_pos) && (x < p.W) && (y < p.H);
+            __nv_bfloat16* o = p.out + ((n * p.H + y) * p.W + x) * p.cout;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + c0, v);
+                tmem_ld_wait();
+                if (c0 == BLOCK_N - 32) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_on_leader(&tmem_empty_bar[acc]);
+                }
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float f8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            f8[j] = __uint_as_float(v[i * 8 + j]) + s_bias[c0 + i * 8 + j];
+                            if (p.relu) f8[j] = fmaxf(f8[j], 0.f);
+                        }
+                        uint4 w4;
+                        w4.x = pack_bf16x2(f8[0], f8[1]);
+                        w4.y = pack_bf16x2(f8[2], f8[3]);
+                        w4.z = pack_bf16x2(f8[4], f8[5]);
+                        w4.w = pack_bf16x2(f8[6], f8[7]);
+                        *reinterpret_cast<uint4*>(o + c0 + i * 8) = w4;
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                        // neither CTA may free TMEM / exit while the pair's MMAs or barriers are live
+    if (warp_idx == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
     static std::mutex mu;
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -401,6 +647,44 @@ extern "C" int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, c
     }
     static const bool no_split = getenv("HG_CONV3X3_NO_NSPLIT") != nullptr;
     if (no_split) block_n = cout;
+    static const bool use_pair = getenv("HG_CONV3X3_PAIR") != nullptr;
+    if (use_pair && cout == 128 && stats == nullptr && kp.num_tiles >= num_sms() / 2) {
+        // paired CTAs: each CTA stages its own 128 positions (+ halo) and half of every weight k-block
+        const int rows = 128 + 2 * kp.P + 2;
+        const int p_boxes = (rows + 255) / 256;
+        const int p_box_rows = ((rows + p_boxes - 1) / p_boxes + 7) / 8 * 8;
+        const int p_region = p_boxes * p_box_rows * 128;
+        const int misc_p = cout * 4 + 1024;
+        int stages = (kSmemLimit - 1024 - 2 * p_region - misc_p) / kPairBStage;
+        if (stages > kPairBStages) stages = kPairBStages;
+        if (stages >= 4) {
+            kp.num_boxes = p_boxes;
+            kp.box_rows = p_box_rows;
+            kp.region_bytes = p_region;
+            kp.b_stages = stages;
+            kp.n_split = 1;
+            kp.num_work = kp.num_tiles;
+            const int smem_pair = 1024 + 2 * kp.region_bytes + stages * kPairBStage + misc_p;
+            const uint64_t rows_total = static_cast<uint64_t>(kp.total_pos) + kp.P;
+            int rc2;
+            if ((rc2 = make_map(&kp.map_a, in_padded, cin, rows_total, kp.box_rows)) != HG_OK) return rc2;
+            if ((rc2 = make_map(&kp.map_b, weight, 9ull * cin, cout, 64)) != HG_OK) return rc2;
+            static std::mutex mu;
+            static unsigned long long done_mask = 0;
+            int dev = 0;
+            HG_CUDA_OK(cudaGetDevice(&dev));
+            {
+                std::lock_guard<std::mutex> lock(mu);
+                if (dev >= 64 || !(done_mask >> dev & 1ull)) {
+                    HG_CUDA_OK(cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+                    if (dev < 64) done_mask |= 1ull << dev;
+                }
+            }
+            const int pairs = kp.num_tiles < num_sms() / 2 ? kp.num_tiles : num_sms() / 2;
+            HG_CUDA_OK(launch_kernel(conv3x3_pair_kernel, dim3(2 * pairs), dim3(256), smem_pair, static_cast<cudaStream_t>(stream), kp));
+            return HG_OK;
+        }
+    }
     kp.n_split = cout / block_n;
     kp.num_work = kp.num_tiles * kp.n_split;
     const int b_stage = block_n * 128;
