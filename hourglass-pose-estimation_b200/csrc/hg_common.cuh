@@ -298,6 +298,17 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                  : "l"(p));
     return r;
 }
+// 256-bit accesses (sm_100): one full 32-byte sector per lane -- for epilogues whose lanes own different rows
+__device__ __forceinline__ void ldg_nc_v8(const void* p, uint32_t* r) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(void* p, const uint32_t* r) {
+    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ uint4 ldg_v4(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void stg_v4(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 

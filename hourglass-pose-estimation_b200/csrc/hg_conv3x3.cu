@@ -49,6 +49,13 @@ struct Params {
     int box_rows, num_boxes, region_bytes;   // halo'd run = num_boxes TMA boxes of box_rows rows
     int b_stages;
     int relu;
+    // K2 + K3 fusion (conv3x3_k3_pair_kernel): the bottleneck's closing 1x1 (128 -> 256) + residual (+ upsample-add)
+    CUtensorMap map_w3;             // (k = 128, cout3 = 256) weights of the 1x1
+    const float* bias3;
+    const __nv_bfloat16* res;       // dense NHWC [n][h][w][256] residual, or null
+    const __nv_bfloat16* up;        // dense NHWC [n][h/2][w/2][256] nearest-upsampled and added, or null
+    __nv_bfloat16* out3;            // dense NHWC [n][h][w][256]
+    int dbg;                        // HG_K3_DEBUG bits (timing experiments only; results are wrong when set)
 };
 
 // kStats: the epilogue also adds the per-channel sum / sum of squares of its results into p.stats (a separate
@@ -538,6 +545,365 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv3x3_pair
     }
 }
 
+// ================================================================================================================
+// K2 + K3 in one kernel (paired CTAs): the 3x3's bf16 result never leaves the SM.  Per CTA: the 3x3 accumulators
+// (2 stages x 128 TMEM columns) are drained by the epilogue warps into a [128 x 128] bf16 K-major operand in shared
+// memory (bias + ReLU = the folded bn3), which the leader multiplies (M = 256 over the pair, N = 256, K = 128) with the
+// resident 1x1 weights (each CTA holds 128 of the 256 output-channel rows) into a third accumulator (256 columns); the
+// same warps then add bias, the residual and optionally the nearest-upsampled low-resolution tensor (both read from
+// global memory at the pixel's dense position) and store the 256-channel result.  Order on the tensor pipe:
+// K2(t), K3(t-1), K2(t+1), ... so the epilogue of tile t overlaps K2(t+1).
+// Warps: 0 A producer, 1 MMA issuer (+TMEM), 2 B producer, 3 W3 loader, 4..11 epilogue (two per TMEM lane quarter: the
+// lower four take the low half of the columns, the upper four the high half).
+// ================================================================================================================
+constexpr int kSlab16 = 128 * kBlockK * 2;              // [128 rows x 64 k] bf16, 128-byte swizzled
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_pair_kernel(const __grid_constant__ Params p) {
+    constexpr int BLOCK_N = 128;
+    constexpr int kTmemCols = 512;                      // K2: 2 x 128 at [0,256); K3: 256 at [256,512)
+    constexpr uint32_t kAcc3 = 256;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;                                    // 2 regions
+    uint8_t* smem_b = smem_a + 2 * p.region_bytes;             // b_stages x 8 KiB
+    uint8_t* smem_a2 = smem_b + p.b_stages * kPairBStage;      // K3's A operand: two K slabs
+    uint8_t* smem_w3 = smem_a2 + 2 * kSlab16;                  // this CTA's 128 rows of W3: two K slabs
+    uint8_t* smem_stage = smem_w3 + 2 * kSlab16;               // 8 warps x 2 private staging buffers of 2 KiB
+    float* s_bias2 = reinterpret_cast<float*>(smem_stage + 2 * kSlab16);
+    float* s_bias3 = s_bias2 + BLOCK_N;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias3 + 256);
+    uint64_t* a_full = bars;                  // [2]   (leader)
+    uint64_t* a_empty = bars + 2;             // [2]
+    uint64_t* b_full = bars + 4;              // [kPairBStages] (leader)
+    uint64_t* b_empty = b_full + kPairBStages;
+    uint64_t* tmem_full_bar = b_empty + kPairBStages;   // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]   (leader; 8 epilogue warps of each CTA)
+    uint64_t* a2_full = tmem_empty_bar + 2;             // (leader; 16 warps)
+    uint64_t* a2_empty = a2_full + 1;
+    uint64_t* acc3_full = a2_empty + 1;
+    uint64_t* acc3_empty = acc3_full + 1;               // (leader; 16 warps)
+    uint64_t* w3_bar = acc3_empty + 1;                  // (leader)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w3_bar + 1);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    for (int i = threadIdx.x; i < BLOCK_N; i += blockDim.x) s_bias2[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias3[i] = p.bias3 ? p.bias3[i] : 0.f;
+    if (warp_idx == 0 && lane == 0) {
+        tma_prefetch_desc(&p.map_a);
+        tma_prefetch_desc(&p.map_b);
+        tma_prefetch_desc(&p.map_w3);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&a_full[s], 1);
+            mbar_init(&a_empty[s], 1);
+            mbar_init(&tmem_full_bar[s], 1);
+            mbar_init(&tmem_empty_bar[s], 16);
+        }
+        for (int s = 0; s < kPairBStages; ++s) {
+            mbar_init(&b_full[s], 1);
+            mbar_init(&b_empty[s], 1);
+        }
+        mbar_init(a2_full, 16);
+        mbar_init(a2_empty, 1);
+        mbar_init(acc3_full, 1);
+        mbar_init(acc3_empty, 16);
+        mbar_init(w3_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp_idx == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+    pdl_launch_dependents();
+
+    const int halo = p.P + 1;
+
+    if (warp_idx == 0) {
+        // ===================== A producer =====================
+        if (elect_one_sync()) {
+            pdl_wait();
+            int it = 0;
+            bool ok = true;
+            for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs) {
+                const long long f0 = static_cast<long long>(p.P) + static_cast<long long>(tile) * kBM + rank * 128;
+                const int row0 = static_cast<int>(f0 - halo);
+                for (int slab = 0; slab < p.slabs; ++slab, ++it) {
+                    const int buf = it & 1;
+                    ok = mbar_wait(&a_empty[buf], ((it >> 1) & 1u) ^ 1u, p.err_word, 0x3901);
+                    if (!ok) break;
+                    if (leader) mbar_arrive_expect_tx(&a_full[buf], static_cast<uint32_t>(2 * p.num_boxes * p.box_rows * 128));
+                    for (int b = 0; b < p.num_boxes; ++b)
+                        tma_load_2d_2sm(smem_a + buf * p.region_bytes + b * p.box_rows * 128, &p.map_a, &a_full[buf],
+                                        slab * kBlockK, row0 + b * p.box_rows);
+                }
+            }
+        }
+    } else if (warp_idx == 2) {
+        // ===================== B producer =====================
+        if (elect_one_sync()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs) {
+                for (int slab = 0; slab < p.slabs && ok; ++slab) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ok = mbar_wait(&b_empty[stage], phase ^ 1u, p.err_word, 0x3b01);
+                        if (!ok) break;
+                        if (leader) mbar_arrive_expect_tx(&b_full[stage], 2 * kPairBStage);
+                        tma_load_2d_2sm(smem_b + stage * kPairBStage, &p.map_b, &b_full[stage], tap * p.cin + slab * kBlockK,
+                                        static_cast<int>(rank) * 64);
+                        if (++stage == p.b_stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 3) {
+        // ===================== W3: this CTA's 128 output-channel rows, resident =====================
+        if (elect_one_sync()) {
+            if (leader) mbar_arrive_expect_tx(w3_bar, 4 * kSlab16);
+            for (int slab = 0; slab < 2; ++slab)
+                tma_load_2d_2sm(smem_w3 + slab * kSlab16, &p.map_w3, w3_bar, slab * kBlockK, static_cast<int>(rank) * 128);
+        }
+    } else if (warp_idx == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && elect_one_sync()) {
+            constexpr uint32_t idesc2 = umma_idesc_bf16(256, BLOCK_N);
+            constexpr uint32_t idesc3 = umma_idesc_bf16(256, 256);
+            const uint32_t a2_base = smem_u32(smem_a2), w3_base = smem_u32(smem_w3);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0, a_it = 0;
+            bool ok = mbar_wait(w3_bar, 0, p.err_word, 0x3a05);
+            auto issue_k3 = [&](int j) -> bool {
+                if (!mbar_wait(a2_full, static_cast<uint32_t>(j & 1), p.err_word, 0x3a06)) return false;
+                if (!mbar_wait(acc3_empty, static_cast<uint32_t>(j & 1) ^ 1u, p.err_word, 0x3a07)) return false;
+                tc_fence_after();
+#pragma unroll
+                for (int slab = 0; slab < 2; ++slab) {
+                    const uint64_t a_desc = umma_desc_sw128(a2_base + slab * kSlab16);
+                    const uint64_t b_desc = umma_desc_sw128(w3_base + slab * kSlab16);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (!(p.dbg & 8)) tc_mma_bf16_2sm(tmem_base + kAcc3, a_desc + 2u * k, b_desc + 2u * k, idesc3, (slab | k) != 0 ? 1u : 0u);
+                }
+                tc_commit_2sm(a2_empty);
+                tc_commit_2sm(acc3_full);
+                return true;
+            };
+            for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs, ++it) {
+                const int acc = it & 1;
+                ok = mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1u) ^ 1u, p.err_word, 0x3a01);
+                if (!ok) break;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+                for (int slab = 0; slab < p.slabs && ok; ++slab, ++a_it) {
+                    const int buf = a_it & 1;
+                    ok = mbar_wait(&a_full[buf], (a_it >> 1) & 1u, p.err_word, 0x3a02);
+                    if (!ok) break;
+                    const uint32_t a_base = smem_u32(smem_a + buf * p.region_bytes);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        ok = mbar_wait(&b_full[stage], phase, p.err_word, 0x3a03);
+                        if (!ok) break;
+                        tc_fence_after();
+                        const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                        const uint32_t row_off = static_cast<uint32_t>(halo + dy * p.P + dx);
+                        const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + stage * kPairBStage));
+                        const uint64_t a_desc = umma_desc_sw128(a_base + row_off * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_bf16_2sm(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc2, (slab | tap | k) != 0 ? 1u : 0u);
+                        tc_commit_2sm(&b_empty[stage]);
+                        if (++stage == p.b_stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    if (ok) tc_commit_2sm(&a_empty[buf]);
+                }
+                if (!ok) break;
+                tc_commit_2sm(&tmem_full_bar[acc]);
+                if (it > 0) ok = issue_k3(it - 1);
+            }
+            if (ok && it > 0) issue_k3(it - 1);
+        }
+    } else if (warp_idx >= 4) {
+        // ===================== epilogue warps: K2 accumulators -> K3 operand, K3 accumulators -> output =====================
+        pdl_wait();
+        const int q = warp_idx & 3;
+        const int ch = (warp_idx - 4) >> 2;                 // column half this warp owns
+        const int row = q * 32 + lane;
+        const long long img_pos = static_cast<long long>(p.H + 1) * p.P;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t a2_row = smem_u32(smem_a2) + ch * kSlab16 + row * 128;
+        long long prev_low = 0;
+        int prev_px = -1;                                    // dense pixel index of this lane's row in the tile being drained
+        // warp-private staging: 2 buffers of [32 rows x 32 channels] bf16 (64-byte rows, 16-byte chunks swizzled so that both
+        // the row-per-lane and the four-lanes-per-row access patterns are bank-conflict free); no CTA-level barriers
+        const uint32_t wstage = smem_u32(smem_stage) + static_cast<uint32_t>(warp_idx - 4) * 4096u;
+        auto sw = [](int r, int chunk) -> uint32_t { return static_cast<uint32_t>(r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4)); };
+        int it = 0;
+        bool ok = true;
+
+        // residual sub-slab `sub` (this warp's 32 rows x 32 channels) -> buffer sub & 1: cp.async, four lanes per row
+        auto fetch_res = [&](int sub) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int idx = k * 32 + lane;
+                const int r = idx >> 2, chunk = idx & 3;
+                const int px = __shfl_sync(0xffffffffu, prev_px, r);
+                if (p.res != nullptr && px >= 0 && !(p.dbg & 2)) {
+                    const __nv_bfloat16* src = p.res + static_cast<long long>(px) * 256 + ch * 128 + sub * 32 + chunk * 8;
+                    const uint32_t dst = wstage + (sub & 1) * 2048u + sw(r, chunk);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+
+        auto drain_k3 = [&](int j) -> bool {
+            // tile j's 1x1 result, 32 channels at a time: the residual waits in the warp's staging buffer, each lane adds its
+            // row in place, and the sub-slab leaves with 64 contiguous bytes per row (eight rows per store instruction)
+            if (!mbar_wait(acc3_full, static_cast<uint32_t>(j & 1), p.err_word, 0x3c03)) return false;
+            tc_fence_after();
+            const bool valid = prev_px >= 0;
+            const __nv_bfloat16* u = p.up != nullptr ? p.up + prev_low * 256 + ch * 128 : nullptr;
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) {
+                const uint32_t buf = wstage + (ph & 1) * 2048u;
+                uint32_t v[32];
+                uint32_t ur[16];
+                if (u != nullptr && valid) {
+                    ldg_nc_v8(u + ph * 32, ur);
+                    ldg_nc_v8(u + ph * 32 + 16, ur + 8);
+                }
+                tmem_ld_32x32(lane_base + kAcc3 + ch * 128 + ph * 32, v);
+                if (ph < 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();                                // every lane's share of this residual sub-slab has landed
+                tmem_ld_wait();
+                if (ph == 3) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_on_leader(acc3_empty);
+                }
+                if (valid && !(p.dbg & 1)) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t addr = buf + sw(lane, i);
+                        uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
+                        if (p.res != nullptr) r4 = lds128(addr);
+                        const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+                        uint32_t o4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int col = ch * 128 + ph * 32 + i * 8 + 2 * e;
+                            float lo = __uint_as_float(v[i * 8 + 2 * e]) + s_bias3[col];
+                            float hi = __uint_as_float(v[i * 8 + 2 * e + 1]) + s_bias3[col + 1];
+                            if (p.res != nullptr) {
+                                lo += bf16_lo_to_f32(rr[e]);
+                                hi += bf16_hi_to_f32(rr[e]);
+                            }
+                            if (u != nullptr) {
+                                lo += bf16_lo_to_f32(ur[i * 4 + e]);
+                                hi += bf16_hi_to_f32(ur[i * 4 + e]);
+                            }
+                            o4[e] = pack_bf16x2(lo, hi);
+                        }
+                        sts128(addr, make_uint4(o4[0], o4[1], o4[2], o4[3]));
+                    }
+                }
+                __syncwarp();                                // the sub-slab is complete
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int idx = k * 32 + lane;
+                    const int r = idx >> 2, chunk = idx & 3;
+                    const int px = __shfl_sync(0xffffffffu, prev_px, r);
+                    if (px >= 0 && !(p.dbg & 1))
+                        stg_v4(p.out3 + static_cast<long long>(px) * 256 + ch * 128 + ph * 32 + chunk * 8, lds128(buf + sw(r, chunk)));
+                }
+                __syncwarp();                                // the buffer may be refilled
+                if (ph < 2) fetch_res(ph + 2);
+            }
+            return true;
+        };
+
+        for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs, ++it) {
+            // the first two residual sub-slabs of the PREVIOUS tile fly while this tile's 3x3 finishes
+            if (it > 0) {
+                fetch_res(0);
+                fetch_res(1);
+            }
+            const int acc = it & 1;
+            ok = mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1u, p.err_word, 0x3c01);
+            if (!ok) break;
+            ok = mbar_wait(a2_empty, static_cast<uint32_t>(it & 1) ^ 1u, p.err_word, 0x3c02);   // K3(it-1) has read the operand buffer
+            if (!ok) break;
+            tc_fence_after();
+            {
+                uint32_t v0[32], v1[32];
+                const uint32_t t2 = lane_base + static_cast<uint32_t>(acc * BLOCK_N + ch * 64);
+                tmem_ld_32x32(t2, v0);
+                tmem_ld_32x32(t2 + 32, v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_on_leader(&tmem_empty_bar[acc]);
+                const float* b2 = s_bias2 + ch * 64;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t* vv = j < 4 ? &v0[j * 8] : &v1[(j - 4) * 8];
+                    uint4 w4;
+                    w4.x = pack_bf16x2_relu(__uint_as_float(vv[0]) + b2[j * 8 + 0], __uint_as_float(vv[1]) + b2[j * 8 + 1]);
+                    w4.y = pack_bf16x2_relu(__uint_as_float(vv[2]) + b2[j * 8 + 2], __uint_as_float(vv[3]) + b2[j * 8 + 3]);
+                    w4.z = pack_bf16x2_relu(__uint_as_float(vv[4]) + b2[j * 8 + 4], __uint_as_float(vv[5]) + b2[j * 8 + 5]);
+                    w4.w = pack_bf16x2_relu(__uint_as_float(vv[6]) + b2[j * 8 + 6], __uint_as_float(vv[7]) + b2[j * 8 + 7]);
+                    if (!(p.dbg & 4)) sts128(a2_row + ((j ^ (row & 7)) << 4), w4);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_on_leader(a2_full);
+            }
+            if (it > 0) {
+                ok = drain_k3(it - 1);
+                if (!ok) break;
+            }
+            // where this tile's row lives in the dense tensors (used when ITS 1x1 result is drained, one iteration later)
+            const long long f = static_cast<long long>(tile) * kBM + rank * 128 + row;
+            const long long n = f / img_pos;
+            const int r = static_cast<int>(f - n * img_pos);
+            const int y = r / p.P, x = r - y * p.P;
+            const bool valid = (f < p.total_pos) && (x < p.W) && (y < p.H);
+            prev_px = valid ? static_cast<int>((n * p.H + y) * p.W + x) : -1;
+            prev_low = (n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+        }
+        if (ok && it > 0) {
+            fetch_res(0);
+            fetch_res(1);
+            drain_k3(it - 1);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
     static std::mutex mu;
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -647,7 +1013,7 @@ extern "C" int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, c
     }
     static const bool no_split = getenv("HG_CONV3X3_NO_NSPLIT") != nullptr;
     if (no_split) block_n = cout;
-    static const bool use_pair = getenv("HG_CONV3X3_PAIR") != nullptr;
+    const bool use_pair = getenv("HG_CONV3X3_PAIR") != nullptr;      // read per call: the tests switch it
     if (use_pair && cout == 128 && stats == nullptr && kp.num_tiles >= num_sms() / 2) {
         // paired CTAs: each CTA stages its own 128 positions (+ halo) and half of every weight k-block
         const int rows = 128 + 2 * kp.P + 2;
@@ -707,4 +1073,89 @@ extern "C" int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, c
         case 64: return launch<64>(kp, smem_bytes, st);
         default: return launch<128>(kp, smem_bytes, st);
     }
+}
+
+// ---- K2 + K3 fused (paired CTAs) ----
+static int k3_pair_geometry(int32_t n, int32_t h, int32_t w, int* boxes, int* box_rows, int* region, int* stages, int* tiles) {
+    using namespace hg;
+    using namespace hg::c3;
+    if (n <= 0 || h <= 0 || w <= 0 || w > 253) return 0;
+    const int P = w + 1;
+    const long long total_pos = static_cast<long long>(n) * (h + 1) * P;
+    const long long num_tiles = (total_pos + kBM - 1) / kBM;
+    if (num_tiles > 0x7fffffffLL / kBM || static_cast<long long>(n) * h * w > 0x7fffffffLL) return 0;     // 32-bit pixel table
+    const int rows = 128 + 2 * P + 2;
+    const int nb = (rows + 255) / 256;
+    const int br = ((rows + nb - 1) / nb + 7) / 8 * 8;
+    const int reg = nb * br * 128;
+    const int misc = (128 + 256 + 256) * 4 + 1024;
+    int st = (kSmemLimit - 1024 - 2 * reg - 6 * kSlab16 - misc) / kPairBStage;
+    if (st > kPairBStages) st = kPairBStages;
+    if (st < 4) return 0;
+    *boxes = nb; *box_rows = br; *region = reg; *stages = st; *tiles = static_cast<int>(num_tiles);
+    return 1;
+}
+
+extern "C" int hg_conv3x3_k3_fusable(int32_t n, int32_t h, int32_t w) {
+    int a, b, c, d, tiles;
+    if (!k3_pair_geometry(n, h, w, &a, &b, &c, &d, &tiles)) return 0;
+    return tiles >= hg::num_sms() / 2 ? 1 : 0;       // at least one tile per CTA pair
+}
+
+extern "C" int hg_conv3x3_k3_fused_bf16(const void* in_padded, const void* w2, const float* b2, const void* w3, const float* b3,
+                                        const void* residual, const void* up_low, void* out, unsigned int* err_word, int32_t n,
+                                        int32_t h, int32_t w, void* stream) {
+    using namespace hg;
+    using namespace hg::c3;
+    Params kp;
+    memset(&kp, 0, sizeof(kp));
+    int tiles = 0;
+    if (!in_padded || !w2 || !w3 || !out || out == residual ||
+        !k3_pair_geometry(n, h, w, &kp.num_boxes, &kp.box_rows, &kp.region_bytes, &kp.b_stages, &tiles) ||
+        (up_low != nullptr && ((h | w) & 1))) {
+        set_last_error("hg_conv3x3_k3_fused_bf16: bad arguments (w <= 253, even h and w with up_low, out != residual)");
+        return HG_ERR_INVALID;
+    }
+    kp.bias = b2;
+    kp.bias3 = b3;
+    {
+        const char* e = getenv("HG_K3_DEBUG");
+        kp.dbg = e ? atoi(e) : 0;
+    }
+    kp.res = static_cast<const __nv_bfloat16*>(residual);
+    kp.up = static_cast<const __nv_bfloat16*>(up_low);
+    kp.out3 = static_cast<__nv_bfloat16*>(out);
+    kp.err_word = err_word;
+    kp.H = h;
+    kp.W = w;
+    kp.P = w + 1;
+    kp.NB = n;
+    kp.cin = 128;
+    kp.cout = 128;
+    kp.slabs = 2;
+    kp.relu = 1;
+    kp.total_pos = static_cast<long long>(n) * (h + 1) * kp.P;
+    kp.num_tiles = tiles;
+    kp.n_split = 1;
+    kp.num_work = tiles;
+    const uint64_t rows_total = static_cast<uint64_t>(kp.total_pos) + kp.P;
+    int rc;
+    if ((rc = make_map(&kp.map_a, in_padded, 128, rows_total, kp.box_rows)) != HG_OK) return rc;
+    if ((rc = make_map(&kp.map_b, w2, 9ull * 128, 128, 64)) != HG_OK) return rc;
+    if ((rc = make_map(&kp.map_w3, w3, 128, 256, 128)) != HG_OK) return rc;
+    static std::mutex mu;
+    static unsigned long long done_mask = 0;
+    int dev = 0;
+    HG_CUDA_OK(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev >= 64 || !(done_mask >> dev & 1ull)) {
+            HG_CUDA_OK(cudaFuncSetAttribute(conv3x3_k3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            if (dev < 64) done_mask |= 1ull << dev;
+        }
+    }
+    const int smem_bytes = 1024 + 2 * kp.region_bytes + kp.b_stages * kPairBStage + 6 * kSlab16 + (128 + 256 + 256) * 4 + 1024;
+    const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+    HG_CUDA_OK(launch_kernel(conv3x3_k3_pair_kernel, dim3(2 * pairs), dim3(384), smem_bytes, static_cast<cudaStream_t>(stream), kp));
+    return HG_OK;
 }

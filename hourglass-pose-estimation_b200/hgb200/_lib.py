@@ -49,6 +49,8 @@ _SIGNATURES = {
     "hg_stem_im2col": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_halo_padded_elems": ([_i32, _i32, _i32, _i32], C.c_int64),
     "hg_conv3x3_halo_bf16": ([_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_conv3x3_k3_fusable": ([_i32, _i32, _i32], C.c_int),
+    "hg_conv3x3_k3_fused_bf16": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp], C.c_int),
     "hg_stem_pack": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_stem_conv": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp], C.c_int),
     "hg_maxpool2x2_nhwc": ([_vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),

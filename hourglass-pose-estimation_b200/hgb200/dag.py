@@ -29,6 +29,7 @@ _WRITES: Dict[str, Tuple[Tuple, Tuple]] = {
     # name: (written positional indices, written keyword names)
     "conv_nhwc": ((), ("out", "out_nchw_f32", "out_halo", "stats", "pool_out")),
     "conv3x3_halo": ((), ("out", "stats")),
+    "conv3x3_k3_fused": ((), ("out",)),
     "dwconv3x3": ((), ("out",)),
     "stem_im2col": ((), ("out",)),
     "stem_pack": ((1,), ("packed",)),

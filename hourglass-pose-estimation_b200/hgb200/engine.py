@@ -47,6 +47,8 @@ def streams_for(rows: int) -> int:
 # The 2x2 max-pool of a hourglass level's input is written by the epilogue of the 1x1 GEMM that produces that input
 # (hg_conv_desc.pool_out) instead of a separate kernel that re-reads it; HG_NO_POOL_FUSION=1 keeps the separate kernel.
 FUSE_POOL = os.environ.get("HG_NO_POOL_FUSION", "0") != "1"
+# K2 + K3 of a bottleneck in one paired-CTA launch (experimental: at parity with the two kernels)
+FUSE_K3 = os.environ.get("HG_FUSE_K3") is not None
 
 
 class _Arena:
@@ -281,6 +283,17 @@ class HourglassEngine:
                                       bytes=pixels * (x.shape[3] + bw.planes) * 2 + bw.w1.numel() * 2))
                 L.append(lambda: ops.conv_nhwc(x, bw.w1, bw.b1, ksize=1, cout=bw.planes, relu=True, in_scale=bw.s1,
                                                in_shift=bw.t1, out_halo=a2h))
+                if (FUSE_K3 and bw.planes == 128 and not bw.downsample and bw.cout == 256
+                        and ops.conv3x3_k3_fusable(bn_, bh_, bw_)):
+                    # K2 + K3 in one launch on CTA pairs: the 3x3's result never leaves the SM (hg_conv3x3_k3_fused_bf16)
+                    out = arena.get((bn_, bh_, bw_, bw.cout))
+                    plan.meta.append(dict(op=f"conv3x3h_k3_fused_{bh_}x{bw_}" + ("_up" if up_low is not None else ""), kind="conv",
+                                          flops=2.0 * pixels * (9 * 128 * 128 + 128 * 256),
+                                          bytes=pixels * (128 + 256 + 256) * 2 + bw.w2.numel() * 2 + bw.w3.numel() * 2))
+                    L.append(lambda: ops.conv3x3_k3_fused(a2h, bw.w2, bw.b2, bw.w3, bw.b3, n=bn_, h=bh_, w=bw_, residual=x,
+                                                          up_low=up_low, out=out))
+                    arena.put_halo(a2h, bn_, bh_, bw_, bw.planes)
+                    return out
                 a3 = arena.get((bn_, bh_, bw_, bw.planes))
                 plan.meta.append(dict(op=f"conv3x3h_k{9 * bw.planes}_n{bw.planes}_{bh_}x{bw_}", kind="conv",
                                       flops=2.0 * pixels * 9 * bw.planes * bw.planes,

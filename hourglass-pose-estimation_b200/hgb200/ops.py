@@ -178,6 +178,35 @@ def conv3x3_halo(x_halo: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
     return out
 
 
+def conv3x3_k3_fusable(n: int, h: int, w: int) -> bool:
+    """True when hg_conv3x3_k3_fused_bf16 suits this size (enough 256-position tiles for the CTA pairs, smem budget)."""
+    return bool(lib.hg_conv3x3_k3_fusable(n, h, w))
+
+
+def conv3x3_k3_fused(x_halo: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, w3: torch.Tensor, b3: torch.Tensor, *,
+                     n: int, h: int, w: int, residual: Optional[torch.Tensor] = None,
+                     up_low: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The tail of a bottleneck in one launch: relu(conv3x3(x_halo) + b2) -> conv1x1 (128 -> 256) + b3 + residual
+    (+ nearest-upsampled up_low) -> dense bf16 NHWC [n,h,w,256]   (hg_conv3x3_k3_fused_bf16)."""
+    _require_cuda(x_halo, w2, b2, w3, b3, residual, up_low, out)
+    if x_halo.numel() != halo_padded_elems(n, h, w, 128) or x_halo.dtype != torch.bfloat16:
+        raise HgError("conv3x3_k3_fused: input is not a halo-padded bf16 buffer of [n,h,w,128]")
+    if tuple(w2.shape) != (128, 9 * 128) or tuple(w3.shape) != (256, 128) or w2.dtype != torch.bfloat16 or w3.dtype != torch.bfloat16:
+        raise HgError(f"conv3x3_k3_fused: weights {tuple(w2.shape)}, {tuple(w3.shape)} != [128,1152], [256,128]")
+    if b2.numel() < 128 or b3.numel() < 256 or b2.dtype != torch.float32 or b3.dtype != torch.float32:
+        raise HgError("conv3x3_k3_fused: biases must be fp32 [128] and [256]")
+    for t, shape, name in ((residual, (n, h, w, 256), "residual"), (up_low, (n, h // 2, w // 2, 256), "up_low"),
+                           (out, (n, h, w, 256), "out")):
+        if t is not None and (tuple(t.shape) != shape or t.dtype != torch.bfloat16 or not t.is_contiguous()):
+            raise HgError(f"conv3x3_k3_fused: {name} must be a contiguous bf16 tensor of shape {shape}")
+    if out is None:
+        out = torch.empty((n, h, w, 256), dtype=torch.bfloat16, device=x_halo.device)
+    lib.check(lib.hg_conv3x3_k3_fused_bf16(_ptr(x_halo), _ptr(w2), _ptr(b2), _ptr(w3), _ptr(b3), _ptr(residual), _ptr(up_low),
+                                           _ptr(out), _ptr(err_word(x_halo.device)), n, h, w, _stream()),
+              "hg_conv3x3_k3_fused_bf16")
+    return out
+
+
 def stem_packed_buffer(n: int, h: int, w: int, device) -> torch.Tensor:
     """Zero-initialised NHWC4 bf16 staging image with 4 px of horizontal padding on both sides."""
     return torch.zeros((n, h, w + 8, 4), dtype=torch.bfloat16, device=device)

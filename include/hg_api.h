@@ -33,7 +33,7 @@ extern "C" {
 #define HG_ERR_ARCH (-3)     /* device is not sm_100 */
 #define HG_ERR_DEVICE (-4)   /* a kernel reported a protocol timeout through its error word */
 
-#define HG_API_VERSION 6
+#define HG_API_VERSION 7
 
 int hg_api_version(void);
 /* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
@@ -72,8 +72,8 @@ typedef struct hg_conv_desc {
     int32_t cin, cin2, cout;
     int32_t ksize;           /* 1 or 3 (stride 1, pad ksize/2)                                  */
     int32_t relu;            /* apply ReLU in the epilogue                                      */
-    int32_t out_halo;        /* 1: `out` is a HALO-PADDED buffer (see hg_conv3x3_halo_bf16); 1x1 only,
-                                needs 128 %% w == 0 and (h*w) %% 128 == 0                          */
+    int32_t out_halo;        /* 1: `out` is a HALO-PADDED buffer (see hg_conv3x3_halo_bf16); 1x1 only, w <= 253,
+                                cout in {64,128} unless 128 %% w == 0 and (h*w) %% 128 == 0        */
     float* stats;            /* optional fp32 [2*cout]: per-channel sum | sum of squares over all pixels of the
                                 epilogue's result, ADDED (atomics) -- the batch statistics the next train-mode
                                 BatchNorm needs (nn.BatchNorm2d in training, src/models/modules.py:30-41), fused
@@ -95,6 +95,19 @@ int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream);
 int64_t hg_halo_padded_elems(int32_t n, int32_t h, int32_t w, int32_t c);
 int hg_conv3x3_halo_bf16(const void* in_padded, const void* weight, const float* bias, void* out, unsigned int* err_word,
                          float* stats /* optional fp32 [2*cout], as hg_conv_desc.stats */, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t relu, void* stream);
+
+/* The tail of a bottleneck in ONE launch (reference src/models/modules.py:38-46: conv2 (3x3, 128->128) -> bn3 -> relu ->
+ * conv3 (1x1, 128->256) -> `out += residual`, plus Hourglass's `up1 + F.interpolate(low3, scale_factor=2)`,
+ * modules.py:90-95, when up_low is given).  The 3x3's bf16 result stays in shared memory as the 1x1's operand; the
+ * kernel runs on CTA pairs (cta_group::2).  in_padded / w2 / b2 as hg_conv3x3_halo_bf16 with cin = cout = 128, relu = 1
+ * (b2 carries the folded bn3); w3: bf16 [256][128], b3: fp32 [256]; residual: dense bf16 NHWC [n][h][w][256] or NULL;
+ * up_low: dense bf16 NHWC [n][h/2][w/2][256] or NULL (h, w even); out: dense bf16 NHWC [n][h][w][256].
+ * hg_conv3x3_k3_fusable returns 1 when the size suits the kernel (enough 256-position tiles to fill the CTA pairs,
+ * shared-memory budget); otherwise run hg_conv3x3_halo_bf16 followed by hg_conv_nhwc_bf16. */
+int hg_conv3x3_k3_fusable(int32_t n, int32_t h, int32_t w);
+int hg_conv3x3_k3_fused_bf16(const void* in_padded, const void* w2, const float* b2, const void* w3, const float* b3,
+                             const void* residual, const void* up_low, void* out, unsigned int* err_word, int32_t n,
+                             int32_t h, int32_t w, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Input preprocessing (the step before the path).  mean3 / std3 are HOST arrays.

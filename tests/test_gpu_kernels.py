@@ -136,6 +136,63 @@ def test_conv3x3_halo(shape, ops, dev):
     assert err <= float(ref.abs().max()) * 2 ** -7, f"err {err} vs scale {float(ref.abs().max())}"
 
 
+def _halo_case(n, h, w, dev, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, h, w, 128, generator=g).to(torch.bfloat16)
+    buf = None
+    from hgb200 import ops as _ops
+    buf = _ops.halo_padded_buffer(n, h, w, 128, dev)
+    _ops.halo_interior(buf, n, h, w, 128).copy_(x.to(dev))
+    w2 = (torch.randn(128, 9 * 128, generator=g) / (3.0 * 128 ** 0.5)).to(torch.bfloat16).to(dev)
+    b2 = (torch.randn(128, generator=g) * 0.5).to(dev)
+    return g, buf, w2, b2
+
+
+@pytest.mark.parametrize("shape", [(40, 64, 64), (64, 64, 48), (300, 16, 16), (41, 30, 22)])
+def test_conv3x3_paired_cta_kernel_is_bit_identical(shape, ops, dev, monkeypatch):
+    """cta_group::2 variant of the halo 3x3 (HG_CONV3X3_PAIR): same MMAs in the same order -> the same bits."""
+    n, h, w = shape
+    _, buf, w2, b2 = _halo_case(n, h, w, dev, seed=31)
+    monkeypatch.delenv("HG_CONV3X3_PAIR", raising=False)
+    want = ops.conv3x3_halo(buf, w2, b2, n=n, h=h, w=w, cin=128, cout=128, relu=True)
+    monkeypatch.setenv("HG_CONV3X3_PAIR", "1")
+    got = ops.conv3x3_halo(buf, w2, b2, n=n, h=h, w=w, cin=128, cout=128, relu=True)
+    torch.cuda.synchronize()
+    ops.check_err_word(dev)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("shape", [(40, 64, 64, True, False), (40, 64, 64, True, True), (64, 64, 48, True, True),
+                                   (300, 16, 16, True, False), (41, 30, 22, False, False), (90, 32, 32, False, True)])
+def test_conv3x3_k3_fused_matches_the_two_kernels(shape, ops, dev):
+    """Bottleneck tail in one launch (3x3 -> bias/ReLU -> 1x1 128->256 + residual (+ upsample-add)) on CTA pairs:
+    bit-identical to hg_conv3x3_halo_bf16 followed by hg_conv_nhwc_bf16 (same roundings, same accumulation order)."""
+    n, h, w, use_res, use_up = shape
+    g, buf, w2, b2 = _halo_case(n, h, w, dev, seed=41)
+    w3 = (torch.randn(256, 128, generator=g) / 128 ** 0.5).to(torch.bfloat16).to(dev)
+    b3 = (torch.randn(256, generator=g) * 0.5).to(dev)
+    res = torch.randn(n, h, w, 256, generator=g).to(torch.bfloat16).to(dev) if use_res else None
+    up = torch.randn(n, h // 2, w // 2, 256, generator=g).to(torch.bfloat16).to(dev) if use_up else None
+    assert ops.conv3x3_k3_fusable(n, h, w)
+    z2 = ops.conv3x3_halo(buf, w2, b2, n=n, h=h, w=w, cin=128, cout=128, relu=True)
+    want = ops.conv_nhwc(z2, w3, b3, ksize=1, cout=256, residual=res, up_low=up)
+    got = ops.conv3x3_k3_fused(buf, w2, b2, w3, b3, n=n, h=h, w=w, residual=res, up_low=up)
+    torch.cuda.synchronize()
+    ops.check_err_word(dev)
+    assert torch.equal(got, want)
+
+
+def test_conv3x3_k3_fused_rejects_what_it_cannot_run(ops, dev):
+    from hgb200 import HgError
+    assert not ops.conv3x3_k3_fusable(2, 8, 8)          # too few tiles for the CTA pairs: the caller keeps the two kernels
+    _, buf, w2, b2 = _halo_case(40, 63, 64, dev, seed=1)
+    w3 = torch.zeros(256, 128, dtype=torch.bfloat16, device=dev)
+    b3 = torch.zeros(256, device=dev)
+    up = torch.zeros(40, 31, 32, 256, dtype=torch.bfloat16, device=dev)
+    with pytest.raises(HgError):
+        ops.conv3x3_k3_fused(buf, w2, b2, w3, b3, n=40, h=63, w=64, up_low=up)        # odd height with an upsample operand
+
+
 @pytest.mark.parametrize("shape", [(2, 64, 64, 256, 128), (3, 32, 32, 256, 128), (1, 128, 128, 64, 64), (4, 16, 16, 256, 128)])
 def test_conv1x1_writes_halo_padded_output(shape, ops, dev):
     no_tf32()
