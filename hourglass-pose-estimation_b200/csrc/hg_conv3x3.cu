@@ -346,6 +346,17 @@ __device__ __forceinline__ void mbar_arrive_on_leader(uint64_t* bar) {
         ::"r"(smem_u32(bar))
         : "memory");
 }
+// Same, without release semantics: for arrivals that only hand TMEM columns back (ordered by tcgen05.fence::before_thread_sync).
+// A cluster-scope RELEASE waits until the thread's earlier global stores are performed -- an epilogue that has just stored its
+// previous sub-slab would hold the accumulator for the store round trip.
+__device__ __forceinline__ void mbar_arrive_on_leader_relaxed(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
 
 constexpr int kPairBStages = 16;
 constexpr int kPairBStage = 64 * kBlockK * 2;          // this CTA's half of a [128 x 64] weight k-block
@@ -776,18 +787,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
         auto drain_k3 = [&](int j) -> bool {
             // tile j's 1x1 result, 32 channels at a time: the residual waits in the warp's staging buffer, each lane adds its
             // row in place, and the sub-slab leaves with 64 contiguous bytes per row (eight rows per store instruction)
-            if (!mbar_wait(acc3_full, static_cast<uint32_t>(j & 1), p.err_word, 0x3c03)) return false;
-            tc_fence_after();
             const bool valid = prev_px >= 0;
             const __nv_bfloat16* u = p.up != nullptr ? p.up + prev_low * 256 + ch * 128 : nullptr;
+            uint32_t ur2[2][16];                             // upsample operand, one phase ahead
+            if (u != nullptr && valid) {
+                ldg_nc_v8(u, ur2[0]);
+                ldg_nc_v8(u + 16, ur2[0] + 8);
+            }
+            if (!mbar_wait(acc3_full, static_cast<uint32_t>(j & 1), p.err_word, 0x3c03)) return false;
+            tc_fence_after();
 #pragma unroll
             for (int ph = 0; ph < 4; ++ph) {
                 const uint32_t buf = wstage + (ph & 1) * 2048u;
                 uint32_t v[32];
-                uint32_t ur[16];
-                if (u != nullptr && valid) {
-                    ldg_nc_v8(u + ph * 32, ur);
-                    ldg_nc_v8(u + ph * 32 + 16, ur + 8);
+                const uint32_t* ur = ur2[ph & 1];
+                if (u != nullptr && valid && ph < 3) {
+                    ldg_nc_v8(u + (ph + 1) * 32, ur2[(ph + 1) & 1]);
+                    ldg_nc_v8(u + (ph + 1) * 32 + 16, ur2[(ph + 1) & 1] + 8);
                 }
                 tmem_ld_32x32(lane_base + kAcc3 + ch * 128 + ph * 32, v);
                 if (ph < 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -797,7 +813,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                 if (ph == 3) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_on_leader(acc3_empty);
+                    if (lane == 0) mbar_arrive_on_leader_relaxed(acc3_empty);
                 }
                 if (valid && !(p.dbg & 1)) {
 #pragma unroll
@@ -860,7 +876,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_on_leader(&tmem_empty_bar[acc]);
+                if (lane == 0) mbar_arrive_on_leader_relaxed(&tmem_empty_bar[acc]);
                 const float* b2 = s_bias2 + ch * 64;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
