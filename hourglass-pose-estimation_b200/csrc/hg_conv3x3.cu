@@ -857,11 +857,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
         };
 
         for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs, ++it) {
-            // the first two residual sub-slabs of the PREVIOUS tile fly while this tile's 3x3 finishes
-            if (it > 0) {
-                fetch_res(0);
-                fetch_res(1);
-            }
             const int acc = it & 1;
             ok = mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1u, p.err_word, 0x3c01);
             if (!ok) break;
@@ -904,12 +899,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
             const bool valid = (f < p.total_pos) && (x < p.W) && (y < p.H);
             prev_px = valid ? static_cast<int>((n * p.H + y) * p.W + x) : -1;
             prev_low = (n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
-        }
-        if (ok && it > 0) {
+            // the first two residual sub-slabs of THIS tile (drained one iteration later) fly while the next tile's 3x3 runs.
+            // Issued here, not before the operand hand-over above: that arrive is a RELEASE, and a release by a thread with
+            // cp.async or global stores in flight waits for them (MEMBAR) on the tensor pipe's critical path.
             fetch_res(0);
             fetch_res(1);
-            drain_k3(it - 1);
         }
+        if (ok && it > 0) drain_k3(it - 1);
     }
 
     tc_fence_before();
