@@ -298,6 +298,18 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                  : "l"(p));
     return r;
 }
+// packed fp32 pairs (sm_100 FADD2): two IEEE additions per instruction, bit-identical to two scalar adds
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    return static_cast<unsigned long long>(__float_as_uint(lo)) | (static_cast<unsigned long long>(__float_as_uint(hi)) << 32);
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float f2_lo(unsigned long long a) { return __uint_as_float(static_cast<uint32_t>(a)); }
+__device__ __forceinline__ float f2_hi(unsigned long long a) { return __uint_as_float(static_cast<uint32_t>(a >> 32)); }
+
 // 256-bit accesses (sm_100): one full 32-byte sector per lane -- for epilogues whose lanes own different rows
 __device__ __forceinline__ void ldg_nc_v8(const void* p, uint32_t* r) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"

@@ -764,19 +764,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
         // warp-private staging: 2 buffers of [32 rows x 32 channels] bf16 (64-byte rows, 16-byte chunks swizzled so that both
         // the row-per-lane and the four-lanes-per-row access patterns are bank-conflict free); no CTA-level barriers
         const uint32_t wstage = smem_u32(smem_stage) + static_cast<uint32_t>(warp_idx - 4) * 4096u;
+        const uint32_t bias3_s = smem_u32(s_bias3), bias2_s = smem_u32(s_bias2);
         auto sw = [](int r, int chunk) -> uint32_t { return static_cast<uint32_t>(r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4)); };
         int it = 0;
         bool ok = true;
 
         // residual sub-slab `sub` (this warp's 32 rows x 32 channels) -> buffer sub & 1: cp.async, four lanes per row
+        // rows this lane moves in the four-lanes-per-row passes (k-th pass: row k*8 + lane/4, chunk lane%4): element offset of
+        // that row's pixel in the 256-channel tensors (+ this warp's channel half + chunk), or -1 for pads; set once per tile
+        long long mv_off[4] = {-1, -1, -1, -1};
         auto fetch_res = [&](int sub) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int idx = k * 32 + lane;
                 const int r = idx >> 2, chunk = idx & 3;
-                const int px = __shfl_sync(0xffffffffu, prev_px, r);
-                if (p.res != nullptr && px >= 0 && !(p.dbg & 2)) {
-                    const __nv_bfloat16* src = p.res + static_cast<long long>(px) * 256 + ch * 128 + sub * 32 + chunk * 8;
+                if (p.res != nullptr && mv_off[k] >= 0 && !(p.dbg & 2)) {
+                    const __nv_bfloat16* src = p.res + mv_off[k] + sub * 32;
                     const uint32_t dst = wstage + (sub & 1) * 2048u + sw(r, chunk);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
                 }
@@ -822,21 +825,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                         uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
                         if (p.res != nullptr) r4 = lds128(addr);
                         const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+                        const uint32_t bs = bias3_s + static_cast<uint32_t>((ch * 128 + ph * 32 + i * 8) * 4);
+                        const float4 ba = lds128f(bs), bb = lds128f(bs + 16);
+                        const float bl[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
                         uint32_t o4[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const int col = ch * 128 + ph * 32 + i * 8 + 2 * e;
-                            float lo = __uint_as_float(v[i * 8 + 2 * e]) + s_bias3[col];
-                            float hi = __uint_as_float(v[i * 8 + 2 * e + 1]) + s_bias3[col + 1];
-                            if (p.res != nullptr) {
-                                lo += bf16_lo_to_f32(rr[e]);
-                                hi += bf16_hi_to_f32(rr[e]);
-                            }
-                            if (u != nullptr) {
-                                lo += bf16_lo_to_f32(ur[i * 4 + e]);
-                                hi += bf16_hi_to_f32(ur[i * 4 + e]);
-                            }
-                            o4[e] = pack_bf16x2(lo, hi);
+                            // (acc + bias) + residual (+ upsampled), two channels per FADD2 -- the order of the two-kernel path
+                            unsigned long long a = f2_add(f2_pack(__uint_as_float(v[i * 8 + 2 * e]), __uint_as_float(v[i * 8 + 2 * e + 1])),
+                                                          f2_pack(bl[2 * e], bl[2 * e + 1]));
+                            if (p.res != nullptr) a = f2_add(a, f2_pack(bf16_lo_to_f32(rr[e]), bf16_hi_to_f32(rr[e])));
+                            if (u != nullptr) a = f2_add(a, f2_pack(bf16_lo_to_f32(ur[i * 4 + e]), bf16_hi_to_f32(ur[i * 4 + e])));
+                            o4[e] = pack_bf16x2(f2_lo(a), f2_hi(a));
                         }
                         sts128(addr, make_uint4(o4[0], o4[1], o4[2], o4[3]));
                     }
@@ -846,9 +846,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                 for (int k = 0; k < 4; ++k) {
                     const int idx = k * 32 + lane;
                     const int r = idx >> 2, chunk = idx & 3;
-                    const int px = __shfl_sync(0xffffffffu, prev_px, r);
-                    if (px >= 0 && !(p.dbg & 1))
-                        stg_v4(p.out3 + static_cast<long long>(px) * 256 + ch * 128 + ph * 32 + chunk * 8, lds128(buf + sw(r, chunk)));
+                    if (mv_off[k] >= 0 && !(p.dbg & 1)) stg_v4(p.out3 + mv_off[k] + ph * 32, lds128(buf + sw(r, chunk)));
                 }
                 __syncwarp();                                // the buffer may be refilled
                 if (ph < 2) fetch_res(ph + 2);
@@ -872,15 +870,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_on_leader_relaxed(&tmem_empty_bar[acc]);
-                const float* b2 = s_bias2 + ch * 64;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t* vv = j < 4 ? &v0[j * 8] : &v1[(j - 4) * 8];
+                    const uint32_t bs = bias2_s + static_cast<uint32_t>((ch * 64 + j * 8) * 4);
+                    const float4 ba = lds128f(bs), bb = lds128f(bs + 16);
+                    const unsigned long long a0 = f2_add(f2_pack(__uint_as_float(vv[0]), __uint_as_float(vv[1])), f2_pack(ba.x, ba.y));
+                    const unsigned long long a1 = f2_add(f2_pack(__uint_as_float(vv[2]), __uint_as_float(vv[3])), f2_pack(ba.z, ba.w));
+                    const unsigned long long a2 = f2_add(f2_pack(__uint_as_float(vv[4]), __uint_as_float(vv[5])), f2_pack(bb.x, bb.y));
+                    const unsigned long long a3 = f2_add(f2_pack(__uint_as_float(vv[6]), __uint_as_float(vv[7])), f2_pack(bb.z, bb.w));
                     uint4 w4;
-                    w4.x = pack_bf16x2_relu(__uint_as_float(vv[0]) + b2[j * 8 + 0], __uint_as_float(vv[1]) + b2[j * 8 + 1]);
-                    w4.y = pack_bf16x2_relu(__uint_as_float(vv[2]) + b2[j * 8 + 2], __uint_as_float(vv[3]) + b2[j * 8 + 3]);
-                    w4.z = pack_bf16x2_relu(__uint_as_float(vv[4]) + b2[j * 8 + 4], __uint_as_float(vv[5]) + b2[j * 8 + 5]);
-                    w4.w = pack_bf16x2_relu(__uint_as_float(vv[6]) + b2[j * 8 + 6], __uint_as_float(vv[7]) + b2[j * 8 + 7]);
+                    w4.x = pack_bf16x2_relu(f2_lo(a0), f2_hi(a0));
+                    w4.y = pack_bf16x2_relu(f2_lo(a1), f2_hi(a1));
+                    w4.z = pack_bf16x2_relu(f2_lo(a2), f2_hi(a2));
+                    w4.w = pack_bf16x2_relu(f2_lo(a3), f2_hi(a3));
                     if (!(p.dbg & 4)) sts128(a2_row + ((j ^ (row & 7)) << 4), w4);
                 }
                 fence_proxy_async_smem();
@@ -899,6 +902,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
             const bool valid = (f < p.total_pos) && (x < p.W) && (y < p.H);
             prev_px = valid ? static_cast<int>((n * p.H + y) * p.W + x) : -1;
             prev_low = (n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int px = __shfl_sync(0xffffffffu, prev_px, k * 8 + (lane >> 2));
+                mv_off[k] = px >= 0 ? static_cast<long long>(px) * 256 + ch * 128 + (lane & 3) * 8 : -1;
+            }
             // the first two residual sub-slabs of THIS tile (drained one iteration later) fly while the next tile's 3x3 runs.
             // Issued here, not before the operand hand-over above: that arrive is a RELEASE, and a release by a thread with
             // cp.async or global stores in flight waits for them (MEMBAR) on the tensor pipe's critical path.

@@ -47,8 +47,10 @@ def streams_for(rows: int) -> int:
 # The 2x2 max-pool of a hourglass level's input is written by the epilogue of the 1x1 GEMM that produces that input
 # (hg_conv_desc.pool_out) instead of a separate kernel that re-reads it; HG_NO_POOL_FUSION=1 keeps the separate kernel.
 FUSE_POOL = os.environ.get("HG_NO_POOL_FUSION", "0") != "1"
-# K2 + K3 of a bottleneck in one paired-CTA launch (experimental: at parity with the two kernels)
-FUSE_K3 = os.environ.get("HG_FUSE_K3") is not None
+# K2 + K3 of a bottleneck (3x3 -> 1x1 + residual / upsample-add) in one paired-CTA launch wherever the level has enough tiles
+# for the CTA pairs: bit-identical to the two kernels, 9-13 % faster on the pair, +4 % on the C2 step.
+# HG_NO_FUSE_K3=1 keeps the two kernels.
+FUSE_K3 = os.environ.get("HG_NO_FUSE_K3") is None
 
 
 class _Arena:
