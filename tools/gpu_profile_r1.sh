@@ -3,7 +3,7 @@
 # ncu's -k matches the kernel's BASE name (no namespace, no template arguments).
 set -x
 mkdir -p gpurun_out
-K='conv1x1_kernel|conv3x3_kernel|conv_gemm_kernel|stem_conv_kernel|stem_pack_kernel|maxpool2x2_kernel|flip_average_kernel|decode_final_kernel|dwconv3x3_kernel'
+K='conv1x1_kernel|conv3x3_kernel|conv3x3_k3_pair_kernel|conv3x3_pair_kernel|conv_gemm_kernel|stem_conv_kernel|stem_pack_kernel|maxpool2x2_kernel|flip_average_kernel|decode_final_kernel|dwconv3x3_kernel'
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1.log 2>&1; echo "pytest exit $?"
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r1.log 2>&1; echo "smoke exit $?"
 python bench.py --steps 10 --warmup 3 --breakdown gpurun_out/breakdown_r1.csv > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; echo "bench exit $?"
