@@ -55,7 +55,6 @@ struct Params {
     const __nv_bfloat16* res;       // dense NHWC [n][h][w][256] residual, or null
     const __nv_bfloat16* up;        // dense NHWC [n][h/2][w/2][256] nearest-upsampled and added, or null
     __nv_bfloat16* out3;            // dense NHWC [n][h][w][256]
-    int dbg;                        // HG_K3_DEBUG bits (timing experiments only; results are wrong when set)
 };
 
 // kStats: the epilogue also adds the per-channel sum / sum of squares of its results into p.stats (a separate
@@ -569,6 +568,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv3x3_pair
 // ================================================================================================================
 constexpr int kSlab16 = 128 * kBlockK * 2;              // [128 rows x 64 k] bf16, 128-byte swizzled
 
+// kRes / kUp: residual / upsample operand present (separate instantiations: no runtime predicates in the issue-bound epilogue)
+template <bool kRes, bool kUp>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_pair_kernel(const __grid_constant__ Params p) {
     constexpr int BLOCK_N = 128;
     constexpr int kTmemCols = 512;                      // K2: 2 x 128 at [0,256); K3: 256 at [256,512)
@@ -708,7 +709,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                     const uint64_t b_desc = umma_desc_sw128(w3_base + slab * kSlab16);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (!(p.dbg & 8)) tc_mma_bf16_2sm(tmem_base + kAcc3, a_desc + 2u * k, b_desc + 2u * k, idesc3, (slab | k) != 0 ? 1u : 0u);
+                        tc_mma_bf16_2sm(tmem_base + kAcc3, a_desc + 2u * k, b_desc + 2u * k, idesc3, (slab | k) != 0 ? 1u : 0u);
                 }
                 tc_commit_2sm(a2_empty);
                 tc_commit_2sm(acc3_full);
@@ -778,7 +779,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
             for (int k = 0; k < 4; ++k) {
                 const int idx = k * 32 + lane;
                 const int r = idx >> 2, chunk = idx & 3;
-                if (p.res != nullptr && mv_off[k] >= 0 && !(p.dbg & 2)) {
+                if (kRes && mv_off[k] >= 0) {
                     const __nv_bfloat16* src = p.res + mv_off[k] + sub * 32;
                     const uint32_t dst = wstage + (sub & 1) * 2048u + sw(r, chunk);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -791,9 +792,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
             // tile j's 1x1 result, 32 channels at a time: the residual waits in the warp's staging buffer, each lane adds its
             // row in place, and the sub-slab leaves with 64 contiguous bytes per row (eight rows per store instruction)
             const bool valid = prev_px >= 0;
-            const __nv_bfloat16* u = p.up != nullptr ? p.up + prev_low * 256 + ch * 128 : nullptr;
+            const __nv_bfloat16* u = kUp ? p.up + prev_low * 256 + ch * 128 : nullptr;
             uint32_t ur2[2][16];                             // upsample operand, one phase ahead
-            if (u != nullptr && valid) {
+            if (kUp && valid) {
                 ldg_nc_v8(u, ur2[0]);
                 ldg_nc_v8(u + 16, ur2[0] + 8);
             }
@@ -804,7 +805,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                 const uint32_t buf = wstage + (ph & 1) * 2048u;
                 uint32_t v[32];
                 const uint32_t* ur = ur2[ph & 1];
-                if (u != nullptr && valid && ph < 3) {
+                if (kUp && valid && ph < 3) {
                     ldg_nc_v8(u + (ph + 1) * 32, ur2[(ph + 1) & 1]);
                     ldg_nc_v8(u + (ph + 1) * 32 + 16, ur2[(ph + 1) & 1] + 8);
                 }
@@ -818,12 +819,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                     __syncwarp();
                     if (lane == 0) mbar_arrive_on_leader_relaxed(acc3_empty);
                 }
-                if (valid && !(p.dbg & 1)) {
+                if (valid) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t addr = buf + sw(lane, i);
                         uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
-                        if (p.res != nullptr) r4 = lds128(addr);
+                        if (kRes) r4 = lds128(addr);
                         const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
                         const uint32_t bs = bias3_s + static_cast<uint32_t>((ch * 128 + ph * 32 + i * 8) * 4);
                         const float4 ba = lds128f(bs), bb = lds128f(bs + 16);
@@ -834,8 +835,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                             // (acc + bias) + residual (+ upsampled), two channels per FADD2 -- the order of the two-kernel path
                             unsigned long long a = f2_add(f2_pack(__uint_as_float(v[i * 8 + 2 * e]), __uint_as_float(v[i * 8 + 2 * e + 1])),
                                                           f2_pack(bl[2 * e], bl[2 * e + 1]));
-                            if (p.res != nullptr) a = f2_add(a, f2_pack(bf16_lo_to_f32(rr[e]), bf16_hi_to_f32(rr[e])));
-                            if (u != nullptr) a = f2_add(a, f2_pack(bf16_lo_to_f32(ur[i * 4 + e]), bf16_hi_to_f32(ur[i * 4 + e])));
+                            if (kRes) a = f2_add(a, f2_pack(bf16_lo_to_f32(rr[e]), bf16_hi_to_f32(rr[e])));
+                            if (kUp) a = f2_add(a, f2_pack(bf16_lo_to_f32(ur[i * 4 + e]), bf16_hi_to_f32(ur[i * 4 + e])));
                             o4[e] = pack_bf16x2(f2_lo(a), f2_hi(a));
                         }
                         sts128(addr, make_uint4(o4[0], o4[1], o4[2], o4[3]));
@@ -846,10 +847,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                 for (int k = 0; k < 4; ++k) {
                     const int idx = k * 32 + lane;
                     const int r = idx >> 2, chunk = idx & 3;
-                    if (mv_off[k] >= 0 && !(p.dbg & 1)) stg_v4(p.out3 + mv_off[k] + ph * 32, lds128(buf + sw(r, chunk)));
+                    if (mv_off[k] >= 0) stg_v4(p.out3 + mv_off[k] + ph * 32, lds128(buf + sw(r, chunk)));
                 }
-                __syncwarp();                                // the buffer may be refilled
-                if (ph < 2) fetch_res(ph + 2);
+                if (ph < 2) {
+                    __syncwarp();                            // the buffer may be refilled
+                    fetch_res(ph + 2);
+                }
             }
             return true;
         };
@@ -884,7 +887,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
                     w4.y = pack_bf16x2_relu(f2_lo(a1), f2_hi(a1));
                     w4.z = pack_bf16x2_relu(f2_lo(a2), f2_hi(a2));
                     w4.w = pack_bf16x2_relu(f2_lo(a3), f2_hi(a3));
-                    if (!(p.dbg & 4)) sts128(a2_row + ((j ^ (row & 7)) << 4), w4);
+                    sts128(a2_row + ((j ^ (row & 7)) << 4), w4);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -1138,10 +1141,6 @@ extern "C" int hg_conv3x3_k3_fused_bf16(const void* in_padded, const void* w2, c
     }
     kp.bias = b2;
     kp.bias3 = b3;
-    {
-        const char* e = getenv("HG_K3_DEBUG");
-        kp.dbg = e ? atoi(e) : 0;
-    }
     kp.res = static_cast<const __nv_bfloat16*>(residual);
     kp.up = static_cast<const __nv_bfloat16*>(up_low);
     kp.out3 = static_cast<__nv_bfloat16*>(out);
@@ -1167,15 +1166,20 @@ extern "C" int hg_conv3x3_k3_fused_bf16(const void* in_padded, const void* w2, c
     static unsigned long long done_mask = 0;
     int dev = 0;
     HG_CUDA_OK(cudaGetDevice(&dev));
+    void (*kern)(Params) = residual ? (up_low ? conv3x3_k3_pair_kernel<true, true> : conv3x3_k3_pair_kernel<true, false>)
+                                    : (up_low ? conv3x3_k3_pair_kernel<false, true> : conv3x3_k3_pair_kernel<false, false>);
     {
         std::lock_guard<std::mutex> lock(mu);
         if (dev >= 64 || !(done_mask >> dev & 1ull)) {
-            HG_CUDA_OK(cudaFuncSetAttribute(conv3x3_k3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            HG_CUDA_OK(cudaFuncSetAttribute(conv3x3_k3_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            HG_CUDA_OK(cudaFuncSetAttribute(conv3x3_k3_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            HG_CUDA_OK(cudaFuncSetAttribute(conv3x3_k3_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+            HG_CUDA_OK(cudaFuncSetAttribute(conv3x3_k3_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
             if (dev < 64) done_mask |= 1ull << dev;
         }
     }
     const int smem_bytes = 1024 + 2 * kp.region_bytes + kp.b_stages * kPairBStage + 6 * kSlab16 + (128 + 256 + 256) * 4 + 1024;
     const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-    HG_CUDA_OK(launch_kernel(conv3x3_k3_pair_kernel, dim3(2 * pairs), dim3(384), smem_bytes, static_cast<cudaStream_t>(stream), kp));
+    HG_CUDA_OK(launch_kernel(kern, dim3(2 * pairs), dim3(384), smem_bytes, static_cast<cudaStream_t>(stream), kp));
     return HG_OK;
 }
