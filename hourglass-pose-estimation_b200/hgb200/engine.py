@@ -48,7 +48,7 @@ def streams_for(rows: int) -> int:
 # (hg_conv_desc.pool_out) instead of a separate kernel that re-reads it; HG_NO_POOL_FUSION=1 keeps the separate kernel.
 FUSE_POOL = os.environ.get("HG_NO_POOL_FUSION", "0") != "1"
 # K2 + K3 of a bottleneck (3x3 -> 1x1 + residual / upsample-add) in one paired-CTA launch wherever the level has enough tiles
-# for the CTA pairs: bit-identical to the two kernels, 9-13 % faster on the pair, +4 % on the C2 step.
+# for the CTA pairs: bit-identical to the two kernels, 10-17 % faster on the pair, +4-5 % on the C2 step.
 # HG_NO_FUSE_K3=1 keeps the two kernels.
 FUSE_K3 = os.environ.get("HG_NO_FUSE_K3") is None
 
