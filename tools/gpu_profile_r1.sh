@@ -14,6 +14,9 @@ python tests/gpu_stock_torch_baseline.py gpurun_out/stock_torch_b200.json > gpur
 # the COCO-shaped configuration (C4: 256x192, J=17): inference forward and training step with per-class breakdowns
 python tools/c4_time.py --breakdown > gpurun_out/c4_infer_r1.log 2>&1; echo "c4 infer exit $?"
 python tools/c4_train_time.py > gpurun_out/c4_train_r1.log 2>&1; echo "c4 train exit $?"
+# paired-CTA kernels against the single-CTA / two-kernel paths (bit level) with timings
+python tools/pair_check.py single > gpurun_out/pair_single_r1.log 2>&1; HG_CONV3X3_PAIR=1 python tools/pair_check.py pair > gpurun_out/pair_pair_r1.log 2>&1; echo "pair check exit $?"
+python tools/k3_check.py > gpurun_out/k3_check_r1.log 2>&1; echo "k3 check exit $?"
 # launch list of ONE pass of the inference step (the eager warm-up pass: same kernels as a graph replay)
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$K" -s 0 -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list_r1.log 2>&1; echo "ncu list exit $?"
 # launch list of the training step's eager recording pass (everything from pack_weights on)
