@@ -17,6 +17,10 @@
 //
 // Per 256 outputs: A traffic 2 x 50 KiB (was 2 x 288 KiB), B traffic 288 KiB (was 576 KiB).
 // Warp roles: 0 = A producer, 1 = MMA issuer + TMEM owner, 2 = B producer, 4..7 = epilogue.
+//
+// Three kernels live here: conv3x3_kernel (one CTA per tile; training and the small levels), conv3x3_pair_kernel (the same
+// GEMM on CTA pairs, cta_group::2: half the shared memory and TMEM per CTA) and conv3x3_k3_pair_kernel, which uses that
+// room to run the bottleneck's closing 1x1 (+ residual / upsample-add) on the 3x3's result without leaving the SM.
 #include "hg_common.cuh"
 #include "../../include/hg_api.h"
 
