@@ -291,7 +291,8 @@ class HourglassEngine:
                     out = arena.get((bn_, bh_, bw_, bw.cout))
                     plan.meta.append(dict(op=f"conv3x3h_k3_fused_{bh_}x{bw_}" + ("_up" if up_low is not None else ""), kind="conv",
                                           flops=2.0 * pixels * (9 * 128 * 128 + 128 * 256),
-                                          bytes=pixels * (128 + 256 + 256) * 2 + bw.w2.numel() * 2 + bw.w3.numel() * 2))
+                                          bytes=pixels * (128 + 256 + 256) * 2 + (pixels * 256 * 2 // 4 if up_low is not None else 0)
+                                          + bw.w2.numel() * 2 + bw.w3.numel() * 2))
                     L.append(lambda: ops.conv3x3_k3_fused(a2h, bw.w2, bw.b2, bw.w3, bw.b3, n=bn_, h=bh_, w=bw_, residual=x,
                                                           up_low=up_low, out=out))
                     arena.put_halo(a2h, bn_, bh_, bw_, bw.planes)
