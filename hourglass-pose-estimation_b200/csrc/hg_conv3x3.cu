@@ -917,6 +917,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
             // the first two residual sub-slabs of THIS tile (drained one iteration later) fly while the next tile's 3x3 runs.
             // Issued here, not before the operand hand-over above: that arrive is a RELEASE, and a release by a thread with
             // cp.async or global stores in flight waits for them (MEMBAR) on the tensor pipe's critical path.
+            __syncwarp();                                    // every lane has read the staging buffers of the tile just drained
             fetch_res(0);
             fetch_res(1);
         }
