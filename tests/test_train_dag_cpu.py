@@ -41,6 +41,22 @@ def test_edges_from_byte_ranges():
     assert d.check_order(range(8)) and not d.check_order([1, 0, 2, 3, 4, 5, 6, 7])
 
 
+def test_every_launch_wrapper_the_plans_use_has_a_footprint_entry():
+    """A wrapper without a _WRITES entry is a BARRIER in the launch DAG (correct but serialising); one whose entry forgets
+    an output is a missed dependency.  The fused bottleneck tail: reads the halo buffer, weights, residual and the
+    low-resolution operand, writes `out` only."""
+    t = lambda *shape: torch.zeros(*shape)
+    halo, w2, b2, w3, b3 = t(100), t(128, 1152), t(128), t(256, 128), t(256)
+    res, up, out = t(2, 4, 4, 256), t(2, 2, 2, 256), t(2, 4, 4, 256)
+    reads, writes = dag.accesses("conv3x3_k3_fused", (halo, w2, b2, w3, b3), dict(n=2, h=4, w=4, residual=res, up_low=up, out=out))
+    region = lambda x: (x.untyped_storage().data_ptr(), 0, x.numel() * 4)
+    assert writes == [region(out)]
+    assert {region(x) for x in (halo, w2, b2, w3, b3, res, up)} == set(reads)
+    for name in ("conv_nhwc", "conv3x3_halo", "conv3x3_k3_fused", "maxpool2x2", "dwconv3x3", "stem_pack", "stem_conv",
+                 "flip_average", "decode_final_preds_into"):
+        assert name in dag._WRITES, name
+
+
 def test_stream_assignment_covers_every_edge():
     rnd = random.Random(0)
     recs = []
