@@ -53,6 +53,29 @@ FUSE_POOL = os.environ.get("HG_NO_POOL_FUSION", "0") != "1"
 FUSE_K3 = os.environ.get("HG_NO_FUSE_K3") is None
 
 
+def _host_copy(t: torch.Tensor) -> torch.Tensor:
+    """CPU copy of a parameter without launching a device kernel: a conv weight that the training engine keeps in
+    [co][kh][kw][ci] order (a channels_last view of the flat store) crosses as the dense tensor it is in memory."""
+    t = t.detach()
+    if t.device.type == "cpu":
+        return t
+    if t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last):
+        return t.permute(0, 2, 3, 1).cpu().permute(0, 3, 1, 2)
+    return t.cpu()
+
+
+def _tensors_of(obj):
+    """Every tensor reachable from a NetWeights / BlockWeights tree, in a deterministic order."""
+    if torch.is_tensor(obj):
+        yield obj
+    elif isinstance(obj, (list, tuple)):
+        for e in obj:
+            yield from _tensors_of(e)
+    elif isinstance(obj, (NetWeights, BlockWeights)):
+        for k in sorted(vars(obj)):
+            yield from _tensors_of(getattr(obj, k))
+
+
 class _Arena:
     """Buffers recycled in emission order.  With the launch DAG a recycled buffer is a write-after-read edge between
     otherwise independent launches, so with several streams reuse is first-in-first-out and only once `depth`
@@ -180,12 +203,25 @@ class HourglassEngine:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise HgError("HourglassEngine needs a CUDA device (no CPU fallback)")
-        w = NetWeights(state_dict, depth)
+        # BatchNorm folding and the GEMM weight layouts are host work on a CPU copy of the parameters (one D2H memcpy per
+        # tensor, no device launches): the device only ever sees the finished bf16 / fp32 operands.
+        w = NetWeights({k: _host_copy(v) for k, v in state_dict.items()}, depth)
         self.w = w
         self.num_stacks = w.num_stacks
         self.num_classes = w.num_classes
         self._to_device(w)
         self.plans: Dict[Tuple[int, int, int, bool], Plan] = {}
+
+    def update_weights(self, state_dict: Dict[str, torch.Tensor]):
+        """Re-fold new parameter values of the SAME architecture into the existing device operands (in place: device
+        pointers, plans and captured graphs stay valid).  What `model.eval()` after a training epoch costs: one D2H copy of
+        the parameters, the host fold, one H2D copy per operand -- no plan rebuild."""
+        new = NetWeights({k: _host_copy(v) for k, v in state_dict.items()}, self.w.depth)
+        old_t, new_t = list(_tensors_of(self.w)), list(_tensors_of(new))
+        if len(old_t) != len(new_t) or any(a.shape != b.shape or a.dtype != b.dtype for a, b in zip(old_t, new_t)):
+            raise HgError("update_weights: the state_dict describes a different architecture")
+        for a, b in zip(old_t, new_t):
+            a.copy_(b, non_blocking=False)
 
     def _to_device(self, obj):
         for k, v in list(vars(obj).items()):

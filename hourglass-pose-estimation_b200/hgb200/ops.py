@@ -22,6 +22,13 @@ def _require_cuda(*ts):
             raise HgError("hgb200 ops need contiguous tensors")
 
 
+def require_device(device):
+    """The path has no CPU fallback: engines call this before they allocate anything."""
+    if torch.device(device).type != "cuda":
+        raise HgError(f"hgb200 runs on CUDA devices only (got '{device}'): there is no CPU fallback; move the model with "
+                      f".to('cuda')")
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

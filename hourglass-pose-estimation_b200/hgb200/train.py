@@ -33,10 +33,7 @@ RMSPROP_EPS = 1e-8
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
-# tests/test_train_plan_cpu.py swaps `ops` for a torch emulation and sets this to exercise the plan's host logic
-# without a GPU; the product path never does (a CPU model raises below).
-_TEST_ALLOW_CPU = False
-_ACT = torch.bfloat16     # activation / GEMM-weight storage type (the same test switches it to fp32 for exact checks)
+_ACT = torch.bfloat16     # activation / GEMM-weight storage type
 # The step's launches are captured as a dependency DAG across this many CUDA streams (hgb200/dag.py);
 # 1 = one chain on one stream.
 STREAMS = int(os.environ.get("HG_TRAIN_STREAMS", "16"))
@@ -385,6 +382,7 @@ class TrainPlan:
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.fwd_bytes = 0
         self.bwd_arena_bytes = 0
+        self.pending_backward = False       # autograd drop-in: a forward whose backward has not run yet
 
     # ---- launch lists
     def _loss_launches(self):
@@ -476,8 +474,7 @@ class TrainPlan:
 class TrainEngine:
     def __init__(self, model: nn.Module, device=None):
         device = torch.device(device or next(model.parameters()).device)
-        if device.type != "cuda" and not _TEST_ALLOW_CPU:
-            raise HgError("TrainEngine needs a CUDA device (no CPU fallback)")
+        ops.require_device(device)            # raises off-CUDA: there is no CPU fallback
         self.device = device
         self.model = model
         for b in model.buffers():
@@ -881,7 +878,7 @@ class TrainEngine:
             # one eager pass with the BN running statistics preserved: loads every kernel and opts in to large
             # shared memory before any graph capture, and records what every launch reads and writes (launch DAG,
             # roofline accounting).  On a side stream when on the GPU.
-            cuda = self.device.type == "cuda"          # else: host-logic tests only (_TEST_ALLOW_CPU)
+            cuda = self.device.type == "cuda"
             bufs = [(b.rm, b.rv, b.nbt) for b in self._bns]
             keep = [(a.clone(), b.clone(), c.clone()) for a, b, c in bufs]
             global ops
@@ -959,8 +956,15 @@ class _TrainFn(torch.autograd.Function):
     def forward(ctx, x, anchor, eng: TrainEngine, use_graph: bool):
         n, _, h, w = x.shape
         plan = eng.plan_for(n, h, w)
+        if plan.pending_backward:
+            # the saved activations live in the plan's static buffers: a second forward of the same shape would
+            # overwrite what the pending backward reads (gradient accumulation over micro-batches of one shape is not
+            # supported on this path; use a larger batch or call backward first)
+            raise HgError("HourglassNet.forward (train mode) re-entered before the backward pass of the previous forward "
+                          "of the same shape has run")
         plan.input.copy_(x, non_blocking=True)
         plan.run("fwd", use_graph)
+        plan.pending_backward = True
         ctx.plan, ctx.eng, ctx.use_graph = plan, eng, use_graph
         return tuple(o.clone() for o in plan.outputs)
 
@@ -973,6 +977,7 @@ class _TrainFn(torch.autograd.Function):
             else:
                 dst.copy_(g, non_blocking=True)
         plan.run("bwd", ctx.use_graph)
+        plan.pending_backward = False
         eng.store.rebind_grads()
         return None, None, None, None
 
@@ -987,9 +992,10 @@ def train_engine(model: nn.Module) -> TrainEngine:
 
 def training_forward(model: nn.Module, x: torch.Tensor):
     dev = next(model.parameters()).device
-    if dev.type != "cuda" and not _TEST_ALLOW_CPU:
-        raise RuntimeError("HourglassNet (B200 build) trains on CUDA only: there is no CPU fallback; "
-                           "move the model with .to('cuda')")
+    try:
+        ops.require_device(dev)
+    except HgError as e:
+        raise RuntimeError(f"HourglassNet (B200 build) trains on CUDA only: {e}") from None
     eng = train_engine(model)
     x = x.to(device=dev, dtype=torch.float32).contiguous()
     if not torch.is_grad_enabled():

@@ -93,7 +93,10 @@ class HourglassNet(nn.Module):
         device = device or next(self.parameters()).device
         key = self._weights_key(device)
         if self._engine is None or self._engine_key != key:
-            self._engine = HourglassEngine(self.state_dict(), device)
+            if self._engine is not None and self._engine.device == torch.device(device):
+                self._engine.update_weights(self.state_dict())         # same module, new values: keep plans and graphs
+            else:
+                self._engine = HourglassEngine(self.state_dict(), device)
             self._engine_key = key
         return self._engine
 

@@ -1,6 +1,6 @@
 """Shared GPU test helpers: torch fp32 references of each fused op and the conv case table.
 
-Used by tests/test_gpu_*.py (pytest, -m gpu) and tests/gpu_debug.py (a verbose sweep that keeps going
+Used by tests/test_gpu_*.py (pytest, -m gpu) and tools/gpu_debug.py (a verbose sweep that keeps going
 after a failure so one gpurun call yields a full picture).
 """
 from __future__ import annotations

@@ -18,7 +18,6 @@ from oracle.make_golden_inputs import train_inputs  # noqa: E402
 def cpu_train(monkeypatch):
     import hgb200.train as tr
     monkeypatch.setattr(tr, "ops", fake_ops)
-    monkeypatch.setattr(tr, "_TEST_ALLOW_CPU", True)
     return tr
 
 

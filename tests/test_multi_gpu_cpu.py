@@ -44,7 +44,7 @@ def _worker(rank, world, port, ret):
         from oracle import train_oracle as T
         from oracle.make_golden_inputs import train_inputs
         from src.models import hg
-        tr.ops, tr._TEST_ALLOW_CPU, tr._ACT = fake_ops, True, torch.float32
+        tr.ops, tr._ACT = fake_ops, torch.float32
         fake_ops.BF = torch.float32
         S, J, B, H, W, lr = 1, 16, 8, 128, 128, 2.5e-4
         sd = make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, seed=0)

@@ -82,7 +82,6 @@ def test_stream_assignment_covers_every_edge():
 def cpu_train(monkeypatch):
     import hgb200.train as tr
     monkeypatch.setattr(tr, "ops", fake_ops)
-    monkeypatch.setattr(tr, "_TEST_ALLOW_CPU", True)
     monkeypatch.setattr(tr, "STREAMS", 6)
     return tr
 

@@ -20,7 +20,6 @@ from oracle.make_golden_inputs import train_inputs
 def cpu_train(monkeypatch):
     import hgb200.train as tr
     monkeypatch.setattr(tr, "ops", fake_ops)
-    monkeypatch.setattr(tr, "_TEST_ALLOW_CPU", True)
     return tr
 
 

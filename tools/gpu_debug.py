@@ -1,5 +1,5 @@
 """Verbose GPU sweep (not a pytest file): runs every conv case and the small kernels, keeps going after
-failures and prints where the errors are.  `python tests/gpu_debug.py [filter]` under gpurun."""
+failures and prints where the errors are.  `python tools/gpu_debug.py [filter]` under gpurun."""
 import os
 import sys
 import time

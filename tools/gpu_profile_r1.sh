@@ -10,7 +10,7 @@ python bench.py --steps 10 --warmup 3 --breakdown gpurun_out/breakdown_r1.csv > 
 python bench.py --workload train --steps 10 --warmup 3 --breakdown gpurun_out/train_breakdown_r1.csv > gpurun_out/bench_train_r1.json 2> gpurun_out/bench_train_r1.err; echo "bench train exit $?"
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_r1.json 2>&1; echo "ref exit $?"
 # stock PyTorch (cuDNN) on the same GPU: the reference network as plain torch ops, fp32 / TF32 / bf16 channels_last
-python tests/gpu_stock_torch_baseline.py gpurun_out/stock_torch_b200.json > gpurun_out/stock_torch.log 2>&1; echo "stock torch exit $?"
+python tools/gpu_stock_torch_baseline.py gpurun_out/stock_torch_b200.json > gpurun_out/stock_torch.log 2>&1; echo "stock torch exit $?"
 # the COCO-shaped configuration (C4: 256x192, J=17): inference forward and training step with per-class breakdowns
 python tools/c4_time.py --breakdown > gpurun_out/c4_infer_r1.log 2>&1; echo "c4 infer exit $?"
 python tools/c4_train_time.py > gpurun_out/c4_train_r1.log 2>&1; echo "c4 train exit $?"

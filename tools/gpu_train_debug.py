@@ -10,7 +10,8 @@ import torch
 import torch.nn.functional as F
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path[:0] = [os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), "hourglass-pose-estimation_b200"), HERE]
+sys.path[:0] = [os.path.dirname(HERE), os.path.join(os.path.dirname(HERE), "hourglass-pose-estimation_b200"),
+                os.path.join(os.path.dirname(HERE), "tests")]
 from hgb200 import ops  # noqa: E402
 
 torch.backends.cudnn.allow_tf32 = False
@@ -140,7 +141,6 @@ def load_emulation():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     mod.ops = fake_ops
-    mod._TEST_ALLOW_CPU = True
     return mod
 
 
