@@ -639,7 +639,7 @@ extern "C" int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream_v) {
     if (rc == HG_OK && d->stats != nullptr) {
         // this general-shape kernel has no fused statistics: one pass over the (L2-resident, just written) result
         rc = hg_colstats_nhwc(d->out, d->stats, d->stats + d->cout, static_cast<int64_t>(d->n) * d->h * d->w, d->cout, d->cout,
-                              stream_v);
+                              0, nullptr, stream_v);
     }
     return rc;
 }

@@ -44,37 +44,103 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return r;
 }
 
-// Block-level combine of per-thread partial sums acc[NV][8] (thread = (pixel lane, 8-channel chunk)) and one
-// atomicAdd per channel: out_v[c] += sum.  out pointers may be null (skipped); channels >= c_valid are skipped.
+// Per-channel reductions run on a 2-D grid: blockIdx.y picks a GROUP of kGroupC8 16-byte chunks (64 channels) and
+// blockIdx.x a SLAB of pixels (pixel lanes x slabs, strided).  A block therefore ends with 64 (x NV) channel sums
+// instead of C, which quarters the number of accumulator updates for C = 256 at the same number of blocks.
+constexpr int kGroupC8 = 8;
+constexpr int kGroupC = kGroupC8 * 8;
+constexpr int kScratchHeader = 16;     // floats reserved at the head of a reduction scratch buffer (arrival counters)
+
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// Block-level combine of per-thread partial sums acc[NV][8] (thread = (pixel lane, 8-channel chunk of this block's
+// group)) and the grid-level sum:  out_v[c] += sum.  out pointers may be null (skipped); channels >= c_valid are skipped.
+//   scratch == nullptr: one atomicAdd per channel per block (order of the additions = order of arrival).
+//   scratch != nullptr: DETERMINISTIC.  Every block stores its partial sums in its own slot of `scratch`, takes a ticket,
+//     and the block that arrives last adds all slots in slab order -- the same fp32 additions in the same order on every
+//     run, whatever the scheduling -- and resets the ticket counter (scratch must be zero before its first use only).
 template <int NV>
-__device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][8], int c8, float* const (&out)[NV], int c_valid) {
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][8], float* const (&out)[NV], int c_valid, float* scratch) {
     __shared__ float sm[NV][kThreads][9];      // +1 padding: conflict-free column reads
+    __shared__ int s_last;
     const int tid = threadIdx.x;
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
         for (int e = 0; e < 8; ++e) sm[v][tid][e] = acc[v][e];
     __syncthreads();
-    const int lanes = kThreads / c8;
-    const int C = c8 * 8;
-    for (int idx = tid; idx < NV * C; idx += kThreads) {
-        const int v = idx / C, c = idx - v * C;
+    constexpr int lanes = kThreads / kGroupC8;
+    const int slabs = gridDim.x;
+    const int c0 = blockIdx.y * kGroupC;
+    const bool direct = scratch == nullptr || slabs == 1;
+    float* part = direct ? nullptr
+                         : scratch + kScratchHeader + (static_cast<size_t>(blockIdx.y) * slabs + blockIdx.x) * (NV * kGroupC);
+    for (int idx = tid; idx < NV * kGroupC; idx += kThreads) {
+        const int v = idx / kGroupC, c = idx - v * kGroupC;
         const int chunk = c >> 3, e = c & 7;
         float s = 0.f;
-        for (int l = 0; l < lanes; ++l) s += sm[v][l * c8 + chunk][e];
-        if (out[v] != nullptr && c < c_valid) atomicAdd(out[v] + c, s);
+        for (int l = 0; l < lanes; ++l) s += sm[v][l * kGroupC8 + chunk][e];
+        if (!direct) {
+            __stcg(part + idx, s);
+        } else if (out[v] != nullptr && c0 + c < c_valid) {
+            if (scratch == nullptr) atomicAdd(out[v] + c0 + c, s);
+            else out[v][c0 + c] += s;          // a single slab: this block is the only writer of these channels
+        }
     }
+    if (direct) return;
+    __threadfence();
+    __syncthreads();
+    unsigned int* counter = reinterpret_cast<unsigned int*>(scratch) + blockIdx.y;
+    if (tid == 0) s_last = atomicAdd(counter, 1u) == static_cast<unsigned int>(slabs - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* all = scratch + kScratchHeader + static_cast<size_t>(blockIdx.y) * slabs * (NV * kGroupC);
+    // two threads per output: even / odd halves of the slab list, each in ascending order, combined in a fixed order
+    const int half = tid / (NV * kGroupC), idx = tid - half * (NV * kGroupC);
+    float s = 0.f;
+    if (half < 2) {
+        const int b0 = half == 0 ? 0 : (slabs + 1) / 2, b1 = half == 0 ? (slabs + 1) / 2 : slabs;
+        int b = b0;
+        for (; b + 4 <= b1; b += 4) {
+            const float v0 = ld_cg_f32(all + static_cast<size_t>(b) * (NV * kGroupC) + idx);
+            const float v1 = ld_cg_f32(all + static_cast<size_t>(b + 1) * (NV * kGroupC) + idx);
+            const float v2 = ld_cg_f32(all + static_cast<size_t>(b + 2) * (NV * kGroupC) + idx);
+            const float v3 = ld_cg_f32(all + static_cast<size_t>(b + 3) * (NV * kGroupC) + idx);
+            s = (((s + v0) + v1) + v2) + v3;
+        }
+        for (; b < b1; ++b) s += ld_cg_f32(all + static_cast<size_t>(b) * (NV * kGroupC) + idx);
+    }
+    __syncthreads();
+    float* comb = &sm[0][0][0];
+    if (half == 1) comb[idx] = s;
+    __syncthreads();
+    if (half == 0) {
+        s += comb[idx];
+        const int v = idx / kGroupC, c = idx - v * kGroupC;
+        if (out[v] != nullptr && c0 + c < c_valid) out[v][c0 + c] += s;
+    }
+    if (tid == 0) *counter = 0u;
 }
+static_assert(kThreads >= 2 * 2 * kGroupC, "final stage: two threads per output");
 
 // ---------------------------------------------------------------- per-channel sum / sum of squares
+// shift != 0: the sums are taken about k[c] = x[pixel 0][c] (sum (x-k), sum (x-k)^2): the variance the BatchNorm derives
+// from them, E[(x-k)^2] - E[x-k]^2, does not cancel catastrophically when |mean| >> std.
 __global__ void __launch_bounds__(kThreads) colstats_kernel(const uint4* __restrict__ x, float* sum, float* sumsq,
-                                                             long long pixels, int c8, int c_valid) {
+                                                             long long pixels, int c8, int c_valid, int shift, float* scratch) {
     pdl_launch_dependents();
     pdl_wait();
-    const int chunk = threadIdx.x % c8, prow = threadIdx.x / c8, lanes = kThreads / c8;
-    float acc[2][8];
+    const int chunk = blockIdx.y * kGroupC8 + threadIdx.x % kGroupC8, prow = threadIdx.x / kGroupC8;
+    constexpr int lanes = kThreads / kGroupC8;
+    float acc[2][8], k[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = 0.f;
+    for (int e = 0; e < 8; ++e) acc[0][e] = acc[1][e] = k[e] = 0.f;
+    if (shift) unpack8(ldg_nc_v4(x + chunk), k);
     // kUnroll independent 16-byte loads in flight per thread: a single load per iteration leaves ~2.4 MB in flight on
     // the whole GPU, well short of the ~6.5 MB that bandwidth x latency asks for
     const long long stride = static_cast<long long>(gridDim.x) * lanes;
@@ -89,8 +155,9 @@ __global__ void __launch_bounds__(kThreads) colstats_kernel(const uint4* __restr
             unpack8(v[u], f);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                acc[0][e] += f[e];
-                acc[1][e] = fmaf(f[e], f[e], acc[1][e]);
+                const float d = f[e] - k[e];
+                acc[0][e] += d;
+                acc[1][e] = fmaf(d, d, acc[1][e]);
             }
         }
     }
@@ -99,12 +166,13 @@ __global__ void __launch_bounds__(kThreads) colstats_kernel(const uint4* __restr
         unpack8(ldg_nc_v4(x + pix * c8 + chunk), f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            acc[0][e] += f[e];
-            acc[1][e] = fmaf(f[e], f[e], acc[1][e]);
+            const float d = f[e] - k[e];
+            acc[0][e] += d;
+            acc[1][e] = fmaf(d, d, acc[1][e]);
         }
     }
     float* const outs[2] = {sum, sumsq};
-    block_channel_reduce<2>(acc, c8, outs, c_valid);
+    block_channel_reduce<2>(acc, outs, c_valid, scratch);
 }
 
 // ---------------------------------------------------------------- train-mode BN + ReLU (forward)
@@ -123,6 +191,7 @@ struct BnFwdParams {
     int n, h, w, c8;
     int halo;               // out is halo-padded [zero row][n][h+1][w+1][c]
     int relu;
+    int shifted;            // sums are taken about k[c] = x[pixel 0][c] (hg_colstats_nhwc with shift)
     float eps, momentum;
 };
 
@@ -134,8 +203,9 @@ __global__ void __launch_bounds__(kThreads) bn_train_fwd_kernel(const BnFwdParam
     const long long pixels = static_cast<long long>(p.n) * p.h * p.w;
     const float inv_n = 1.f / static_cast<float>(pixels);
     for (int c = threadIdx.x; c < C; c += kThreads) {
-        const float mean = p.sums[c] * inv_n;
-        const float var = fmaxf(p.sums[C + c] * inv_n - mean * mean, 0.f);
+        const float m1 = p.sums[c] * inv_n;
+        const float var = fmaxf(p.sums[C + c] * inv_n - m1 * m1, 0.f);
+        const float mean = p.shifted ? m1 + __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.x)[c]) : m1;
         const float invstd = rsqrtf(var + p.eps);
         const float sc = p.gamma[c] * invstd;
         const float sh = p.beta[c] - mean * sc;
@@ -193,11 +263,12 @@ __global__ void __launch_bounds__(kThreads) bn_train_fwd_kernel(const BnFwdParam
 // dY = dz * [x*scale + shift > 0];  s1 = sum dY;  s2 = sum dY * xhat,  xhat = (x - mean) * invstd
 __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ x,
                                                                   const float* __restrict__ saved, float* sums,
-                                                                  long long pixels, int c8, int relu) {
+                                                                  long long pixels, int c8, int relu, float* scratch) {
     pdl_launch_dependents();
     pdl_wait();
     const int C = c8 * 8;
-    const int chunk = threadIdx.x % c8, prow = threadIdx.x / c8, lanes = kThreads / c8;
+    const int chunk = blockIdx.y * kGroupC8 + threadIdx.x % kGroupC8, prow = threadIdx.x / kGroupC8;
+    constexpr int lanes = kThreads / kGroupC8;
     float mean[8], invstd[8], sc[8], sh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -245,7 +316,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const uint4* __
         }
     }
     float* const outs[2] = {sums, sums + C};
-    block_channel_reduce<2>(acc, c8, outs, C);
+    block_channel_reduce<2>(acc, outs, C, scratch);
 }
 
 // ---------------------------------------------------------------- BN + ReLU backward, pass 2
@@ -566,23 +637,38 @@ using namespace hg::tr;
 
 static bool bn_channels_ok(int c) { return c == 64 || c == 128 || c == 256; }
 
+// slabs of a per-channel reduction over `pixels` pixels of a c-channel tensor (grid.x; grid.y = c / 64 groups)
+static int reduce_slabs(long long pixels, int c) {
+    constexpr int lanes = kThreads / kGroupC8;
+    const int groups = c / kGroupC;
+    long long cap = static_cast<long long>(num_sms()) * kReducePerSm / groups;
+    if (cap > 160) cap = 160;            // the deterministic final stage reads one slot per slab
+    if (cap < 1) cap = 1;
+    const long long need = (pixels + lanes - 1) / lanes;
+    return static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+extern "C" int64_t hg_colreduce_scratch_bytes(int64_t pixels, int32_t c) {
+    if (pixels <= 0 || c <= 0 || c % kGroupC != 0) return 0;
+    return static_cast<int64_t>(sizeof(float)) * (kScratchHeader + static_cast<int64_t>(c / kGroupC) * reduce_slabs(pixels, c) * 2 * kGroupC);
+}
+
 extern "C" int hg_colstats_nhwc(const void* x, float* sum, float* sumsq, int64_t pixels, int32_t c, int32_t c_valid,
-                                void* stream) {
+                                int32_t shift, float* scratch, void* stream) {
     if (!x || pixels <= 0 || !bn_channels_ok(c) || c_valid <= 0 || c_valid > c || !aligned16(x)) {
         set_last_error("hg_colstats_nhwc: need c in {64,128,256}, 16-byte aligned input");
         return HG_ERR_INVALID;
     }
-    const int lanes = kThreads / (c / 8);
-    HG_CUDA_OK(launch_kernel(colstats_kernel, dim3(grid_for((pixels + lanes - 1) / lanes, kReducePerSm)), dim3(kThreads), 0,
+    HG_CUDA_OK(launch_kernel(colstats_kernel, dim3(reduce_slabs(pixels, c), c / kGroupC), dim3(kThreads), 0,
                              static_cast<cudaStream_t>(stream), static_cast<const uint4*>(x), sum, sumsq,
-                             static_cast<long long>(pixels), c / 8, c_valid));
+                             static_cast<long long>(pixels), c / 8, c_valid, shift, scratch));
     return HG_OK;
 }
 
 extern "C" int hg_bn_train_fwd(const void* x, const float* sums, const float* gamma, const float* beta, float* running_mean,
                                float* running_var, int64_t* num_batches_tracked, float* saved, void* out, int32_t n,
-                               int32_t h, int32_t w, int32_t c, int32_t out_halo, int32_t relu, float eps, float momentum,
-                               void* stream) {
+                               int32_t h, int32_t w, int32_t c, int32_t out_halo, int32_t relu, int32_t shifted, float eps,
+                               float momentum, void* stream) {
     if (!x || !sums || !gamma || !beta || !saved || !out || n <= 0 || h <= 0 || w <= 0 || !bn_channels_ok(c) ||
         !aligned16(x) || !aligned16(out)) {
         set_last_error("hg_bn_train_fwd: need c in {64,128,256}, 16-byte aligned tensors");
@@ -601,6 +687,7 @@ extern "C" int hg_bn_train_fwd(const void* x, const float* sums, const float* ga
     p.n = n; p.h = h; p.w = w; p.c8 = c / 8;
     p.halo = out_halo;
     p.relu = relu;
+    p.shifted = shifted;
     p.eps = eps;
     p.momentum = momentum;
     const long long items = static_cast<long long>(n) * h * w * (c / 8);
@@ -610,15 +697,14 @@ extern "C" int hg_bn_train_fwd(const void* x, const float* sums, const float* ga
 }
 
 extern "C" int hg_bn_bwd_reduce(const void* dz, const void* x, const float* saved, float* sums, int64_t pixels, int32_t c,
-                                int32_t relu, void* stream) {
+                                int32_t relu, float* scratch, void* stream) {
     if (!dz || !x || !saved || !sums || pixels <= 0 || !bn_channels_ok(c) || !aligned16(dz) || !aligned16(x)) {
         set_last_error("hg_bn_bwd_reduce: need c in {64,128,256}, 16-byte aligned tensors");
         return HG_ERR_INVALID;
     }
-    const int lanes = kThreads / (c / 8);
-    HG_CUDA_OK(launch_kernel(bn_bwd_reduce_kernel, dim3(grid_for((pixels + lanes - 1) / lanes, kReducePerSm)), dim3(kThreads), 0,
+    HG_CUDA_OK(launch_kernel(bn_bwd_reduce_kernel, dim3(reduce_slabs(pixels, c), c / kGroupC), dim3(kThreads), 0,
                              static_cast<cudaStream_t>(stream), static_cast<const uint4*>(dz), static_cast<const uint4*>(x),
-                             saved, sums, static_cast<long long>(pixels), c / 8, relu));
+                             saved, sums, static_cast<long long>(pixels), c / 8, relu, scratch));
     return HG_OK;
 }
 

@@ -258,7 +258,7 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t r
 
 extern "C" int hg_wgrad_bf16(const void* dout, const void* z, float* dw, unsigned int* err_word, int64_t rows, int32_t co,
                              int32_t co_first, int32_t co_valid, int32_t ci, int32_t ci_valid, int32_t taps, int32_t halo_pitch, int32_t ld,
-                             int32_t tap_stride, void* stream) {
+                             int32_t tap_stride, int32_t max_ctas_arg, void* stream) {
     using namespace hg;
     using namespace hg::wg;
     if (!dout || !z || !dw || rows <= 0 || rows > 0x7fffff00LL || co <= 0 || co > 256 || ci <= 0 || ci > 256 ||
@@ -306,7 +306,10 @@ extern "C" int hg_wgrad_bf16(const void* dout, const void* z, float* dw, unsigne
     // a quarter of the SMs (36 CTAs; HG_WGRAD_CTAS overrides) -- which also quarters the fp32 red.add traffic, every CTA
     // adding a full [cout x cin] tile at its end.  Measured on B200 (training step, batch 32, 8 streams): 24.9 / 24.5 /
     // 24.1 / 24.0 / 23.8 / 24.1 / 25.0 ms for 148 / 96 / 72 / 48 / 36 / 24 / 16 CTAs.
-    static const int max_ctas = getenv("HG_WGRAD_CTAS") ? atoi(getenv("HG_WGRAD_CTAS")) : 36;
+    static const int env_ctas = getenv("HG_WGRAD_CTAS") ? atoi(getenv("HG_WGRAD_CTAS")) : 36;
+    // max_ctas_arg > 0 overrides; 1 = no split along the pixels at all: every dW element is then produced by ONE CTA in
+    // one fixed accumulation order (deterministic, for validation runs; slow)
+    const int max_ctas = max_ctas_arg > 0 ? max_ctas_arg : env_ctas;
     constexpr int min_kb = 8;
     long long chunks = (max_ctas > 0 ? (max_ctas < num_sms() ? max_ctas : num_sms()) : num_sms()) / kp.tap_groups;
     if (chunks > total_kb / min_kb) chunks = total_kb / min_kb;

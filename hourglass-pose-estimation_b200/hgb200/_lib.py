@@ -67,10 +67,11 @@ _SIGNATURES = {
     "hg_gaussian_target": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_jmse_loss": ([C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32,
                       _f32, _vp], C.c_int),
-    "hg_colstats_nhwc": ([_vp, _vp, _vp, _i64, _i32, _i32, _vp], C.c_int),
-    "hg_bn_train_fwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp],
-                        C.c_int),
-    "hg_bn_bwd_reduce": ([_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp], C.c_int),
+    "hg_colreduce_scratch_bytes": ([_i64, _i32], C.c_int64),
+    "hg_colstats_nhwc": ([_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp], C.c_int),
+    "hg_bn_train_fwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _f32,
+                         _vp], C.c_int),
+    "hg_bn_bwd_reduce": ([_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp], C.c_int),
     "hg_bn_bwd_apply": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_normalize_u8_nhwc": ([_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp], C.c_int),
     "hg_preprocess_frames_u8": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
@@ -83,7 +84,7 @@ _SIGNATURES = {
     "hg_pack_weights": ([_vp, _i32, _i32, _vp], C.c_int),
     "hg_rmsprop_step": ([_vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp], C.c_int),
     "hg_small_gemm_f32": ([_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f32, _vp], C.c_int),
-    "hg_wgrad_bf16": ([_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
+    "hg_wgrad_bf16": ([_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp], C.c_int),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

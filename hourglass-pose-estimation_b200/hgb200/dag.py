@@ -38,9 +38,9 @@ _WRITES: Dict[str, Tuple[Tuple, Tuple]] = {
     "decode_final_preds_into": ((3,), ("out",)),
     "normalize_u8": ((), ("out", "packed")),
     "maxpool2x2": ((1,), ("out",)),
-    "colstats": ((1, 2), ("sum_out", "sumsq_out")),
+    "colstats": ((1, 2), ("sum_out", "sumsq_out", "scratch")),
     "bn_train_fwd": ((4, 5, 6, 7, 8), ()),
-    "bn_bwd_reduce": ((3,), ()),
+    "bn_bwd_reduce": ((3,), ("scratch",)),
     "bn_bwd_apply": ((4,), ("dgamma", "dbeta")),
     "wgrad": ((2,), ()),
     "dwconv3x3_wgrad": ((2,), ()),

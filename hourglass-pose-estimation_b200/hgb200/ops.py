@@ -469,7 +469,7 @@ def jmse_loss(preds: Sequence[torch.Tensor], target: Optional[torch.Tensor], tar
 # ------------------------------------------------------------------------------------------------ training
 def wgrad(dout: torch.Tensor, z: torch.Tensor, dw: torch.Tensor, *, co_valid: Optional[int] = None, co_first: int = 0,
           ci_valid: Optional[int] = None, taps: int = 1, halo_pitch: int = 0, ld: Optional[int] = None,
-          tap_stride: Optional[int] = None) -> torch.Tensor:
+          tap_stride: Optional[int] = None, max_ctas: int = 0) -> torch.Tensor:
     """dw (fp32, pre-zeroed or partial) += dout^T . z over rows (hg_wgrad_bf16).
 
     dout: bf16 [..., co], z: bf16 [..., ci] with the same number of rows (taps=9: both halo-padded flat
@@ -489,36 +489,44 @@ def wgrad(dout: torch.Tensor, z: torch.Tensor, dw: torch.Tensor, *, co_valid: Op
     if dw.numel() < (co_valid - co_first - 1) * ld + (taps - 1) * tap_stride + ci_valid:
         raise HgError("wgrad: dw too small")
     lib.check(lib.hg_wgrad_bf16(_ptr(dout), _ptr(z), _ptr(dw), _ptr(err_word(dout.device)), rows, co, co_first, co_valid, ci,
-                                ci_valid, taps, halo_pitch, ld, tap_stride, _stream()), "hg_wgrad_bf16")
+                                ci_valid, taps, halo_pitch, ld, tap_stride, int(max_ctas), _stream()), "hg_wgrad_bf16")
     return dw
 
 
-def colstats(x: torch.Tensor, sum_out: torch.Tensor, sumsq_out: Optional[torch.Tensor] = None, c_valid: Optional[int] = None):
-    """sum_out[c] += sum over pixels of x[..., c] (and sumsq_out[c] += sum of squares); x bf16 NHWC."""
-    _require_cuda(x, sum_out, sumsq_out)
+def colreduce_scratch(pixels: int, c: int, device) -> torch.Tensor:
+    """Zeroed scratch buffer for the deterministic form of colstats / bn_bwd_reduce (one per launch site)."""
+    return torch.zeros(int(lib.hg_colreduce_scratch_bytes(int(pixels), int(c))) // 4, dtype=torch.float32, device=device)
+
+
+def colstats(x: torch.Tensor, sum_out: torch.Tensor, sumsq_out: Optional[torch.Tensor] = None, c_valid: Optional[int] = None,
+             *, shift: bool = False, scratch: Optional[torch.Tensor] = None):
+    """sum_out[c] += sum over pixels of x[..., c] (and sumsq_out[c] += sum of squares); x bf16 NHWC.
+    shift: sums about x[pixel 0] (see hg_colstats_nhwc); scratch: deterministic fixed-order reduction."""
+    _require_cuda(x, sum_out, sumsq_out, scratch)
     c = x.shape[-1]
     lib.check(lib.hg_colstats_nhwc(_ptr(x), _ptr(sum_out), _ptr(sumsq_out), x.numel() // c, c, c if c_valid is None else c_valid,
-                                   _stream()), "hg_colstats_nhwc")
+                                   int(shift), _ptr(scratch), _stream()), "hg_colstats_nhwc")
 
 
 def bn_train_fwd(x: torch.Tensor, sums: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
                  running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor],
                  num_batches_tracked: Optional[torch.Tensor], saved: torch.Tensor, out: torch.Tensor, *, halo: bool = False,
-                 relu: bool = True, eps: float = 1e-5, momentum: float = 0.1):
+                 relu: bool = True, eps: float = 1e-5, momentum: float = 0.1, shifted: bool = False):
     """Train-mode BatchNorm2d(+ReLU) of a dense bf16 NHWC tensor from batch sums (hg_bn_train_fwd)."""
     _require_cuda(x, sums, gamma, beta, running_mean, running_var, num_batches_tracked, saved, out)
     n, h, w, c = x.shape
     lib.check(lib.hg_bn_train_fwd(_ptr(x), _ptr(sums), _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
                                   _ptr(num_batches_tracked), _ptr(saved), _ptr(out), n, h, w, c, int(halo), int(relu),
-                                  C.c_float(eps), C.c_float(momentum), _stream()), "hg_bn_train_fwd")
+                                  int(shifted), C.c_float(eps), C.c_float(momentum), _stream()), "hg_bn_train_fwd")
     return out
 
 
-def bn_bwd_reduce(dz: torch.Tensor, x: torch.Tensor, saved: torch.Tensor, sums: torch.Tensor, relu: bool = True):
-    _require_cuda(dz, x, saved, sums)
+def bn_bwd_reduce(dz: torch.Tensor, x: torch.Tensor, saved: torch.Tensor, sums: torch.Tensor, relu: bool = True,
+                  scratch: Optional[torch.Tensor] = None):
+    _require_cuda(dz, x, saved, sums, scratch)
     c = x.shape[-1]
-    lib.check(lib.hg_bn_bwd_reduce(_ptr(dz), _ptr(x), _ptr(saved), _ptr(sums), x.numel() // c, c, int(relu), _stream()),
-              "hg_bn_bwd_reduce")
+    lib.check(lib.hg_bn_bwd_reduce(_ptr(dz), _ptr(x), _ptr(saved), _ptr(sums), x.numel() // c, c, int(relu), _ptr(scratch),
+                                   _stream()), "hg_bn_bwd_reduce")
 
 
 def bn_bwd_apply(dz: torch.Tensor, x: torch.Tensor, saved: torch.Tensor, sums: torch.Tensor, out: torch.Tensor, *,

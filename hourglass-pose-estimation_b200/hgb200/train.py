@@ -51,6 +51,14 @@ FUSED_STATS = os.environ.get("HG_BN_STATS_FUSED", "0") == "1"
 # (hg_conv_desc.pool_out); HG_NO_POOL_FUSION=1 keeps the separate pool kernel.
 FUSE_POOL = os.environ.get("HG_NO_POOL_FUSION", "0") != "1"
 FUSED_STATS_MAX_PIXELS = int(os.environ.get("HG_BN_STATS_MAX_PIXELS", "32768"))
+# HG_DETERMINISTIC=1: every cross-CTA reduction of the step runs in a fixed order -- BatchNorm statistics, BatchNorm backward
+# sums and bias gradients through per-launch scratch slots added by the last CTA to arrive (hg_colstats_nhwc / hg_bn_bwd_reduce
+# with `scratch`), weight gradients without the split over the pixels (hg_wgrad_bf16 max_ctas = 1) -- so two runs of the step,
+# on one stream or across the launch DAG's streams, with or without programmatic dependent launch, give BIT-IDENTICAL
+# heat maps, gradients and parameters.  That is the race check of the launch DAG (tests/test_gpu_train.py); it costs a
+# couple of microseconds per reduction and serialises the weight-gradient GEMMs, so the default is the atomic form, whose
+# results differ from run to run by the order of fp32 additions only.
+DETERMINISTIC = os.environ.get("HG_DETERMINISTIC", "0") == "1"
 
 
 def _pad(v: int, m: int) -> int:
@@ -383,6 +391,9 @@ class TrainPlan:
         self.fwd_bytes = 0
         self.bwd_arena_bytes = 0
         self.pending_backward = False       # autograd drop-in: a forward whose backward has not run yet
+        self.deterministic = False
+        self.keep: List[torch.Tensor] = []
+        self.scr = lambda t: None
 
     # ---- launch lists
     def _loss_launches(self):
@@ -556,6 +567,17 @@ class TrainEngine:
         dev = self.device
         F, nodes = plan.fwd, plan.nodes
         fwd_bytes = [0]
+        plan.deterministic = DETERMINISTIC
+
+        def scr(t):
+            """Per-launch-site scratch of the fixed-order reductions over the pixels of NHWC tensor `t` (None: atomics)."""
+            if not plan.deterministic:
+                return None
+            s = ops.colreduce_scratch(t.numel() // t.shape[-1], t.shape[-1], dev)
+            plan.keep.append(s)
+            return s
+
+        plan.scr = scr
 
         def new(shape, dtype=None):
             dtype = dtype or _ACT
@@ -576,9 +598,12 @@ class TrainEngine:
                     x.sums, have_stats = bn.sums, True
                 x = x.data
             if not have_stats:
-                F.append(lambda: ops.colstats(x, bn.sums[:bn.c], bn.sums[bn.c:]))
+                # sums about x[pixel 0]: no cancellation in E[x^2] - E[x]^2 when |mean| >> std
+                s = scr(x)
+                F.append(lambda: ops.colstats(x, bn.sums[:bn.c], bn.sums[bn.c:], shift=True, scratch=s))
+            shifted = not have_stats
             F.append(lambda: ops.bn_train_fwd(x, bn.sums, bn.gamma, bn.beta, bn.rm, bn.rv, bn.nbt, bn.saved, out, halo=halo,
-                                              relu=True, eps=bn.eps, momentum=bn.momentum))
+                                              relu=True, eps=bn.eps, momentum=bn.momentum, shifted=shifted))
 
         def block(blk: _Block, x: _T, up_low: Optional[_T] = None) -> _T:
             nb, hh_, ww_, cin = x.data.shape
@@ -726,8 +751,12 @@ class TrainEngine:
         def dgrad1x1(g, wd, cout, out, residual=None):
             B.append(lambda: ops.conv_nhwc(g, wd, None, ksize=1, cout=cout, residual=residual, out=out))
 
+        scr = plan.scr
+        wg_ctas = 1 if plan.deterministic else 0
+
         def bn_bwd(bn: _Bn, dz, xdata, out, *, add1=None, add2=None, halo=False):
-            B.append(lambda: ops.bn_bwd_reduce(dz, xdata, bn.saved, bn.bsums))
+            s = scr(xdata)
+            B.append(lambda: ops.bn_bwd_reduce(dz, xdata, bn.saved, bn.bsums, scratch=s))
             B.append(lambda: ops.bn_bwd_apply(dz, xdata, bn.saved, bn.bsums, out, add1=add1, add2=add2, dgamma=bn.ggamma,
                                               dbeta=bn.gbeta, halo=halo))
 
@@ -745,11 +774,11 @@ class TrainEngine:
                     if not acc:
                         low.grad = arena.get(low.data.shape)
                     B.append(lambda gy=gy, lg=low.grad, acc=acc: ops.sumpool2x2(gy, lg, accumulate=acc))
-                B.append(lambda gy=gy, blk=blk: ops.colstats(gy, blk.c3.gb))
-                B.append(lambda gy=gy, blk=blk, z3=node["z3"]: ops.wgrad(gy, z3, blk.c3.gw))
+                B.append(lambda gy=gy, blk=blk, s=scr(gy): ops.colstats(gy, blk.c3.gb, scratch=s))
+                B.append(lambda gy=gy, blk=blk, z3=node["z3"]: ops.wgrad(gy, z3, blk.c3.gw, max_ctas=wg_ctas))
                 if blk.ds is not None:
-                    B.append(lambda gy=gy, blk=blk: ops.colstats(gy, blk.ds.gb))
-                    B.append(lambda gy=gy, blk=blk, xd=x.data: ops.wgrad(gy, xd, blk.ds.gw))
+                    B.append(lambda gy=gy, blk=blk, s=scr(gy): ops.colstats(gy, blk.ds.gb, scratch=s))
+                    B.append(lambda gy=gy, blk=blk, xd=x.data: ops.wgrad(gy, xd, blk.ds.gw, max_ctas=wg_ctas))
                 dz3 = arena.get((nb, hh_, ww_, pl))
                 dgrad1x1(gy, blk.c3.wd, pl, dz3)
                 if blk.c2.depthwise:
@@ -765,7 +794,7 @@ class TrainEngine:
                     bn_bwd(blk.bn3, dz3, node["a2"], da2h, halo=True)
                     arena.put(dz3)
                     B.append(lambda da2h=da2h, z2h=node["z2h"], blk=blk, P=ww_ + 1, pl=pl:
-                             ops.wgrad(da2h.view(-1, pl), z2h.view(-1, pl), blk.c2.gw, taps=9, halo_pitch=P))
+                             ops.wgrad(da2h.view(-1, pl), z2h.view(-1, pl), blk.c2.gw, taps=9, halo_pitch=P, max_ctas=wg_ctas))
                     dz2 = arena.get((nb, hh_, ww_, pl))
                     B.append(lambda da2h=da2h, blk=blk, dz2=dz2, nb=nb, hh_=hh_, ww_=ww_, pl=pl:
                              ops.conv3x3_halo(da2h, blk.c2.wd, None, n=nb, h=hh_, w=ww_, cin=pl, cout=pl, out=dz2))
@@ -773,7 +802,7 @@ class TrainEngine:
                 da1 = arena.get((nb, hh_, ww_, pl))
                 bn_bwd(blk.bn2, dz2, node["a1"], da1)
                 arena.put(dz2)
-                B.append(lambda da1=da1, z1=node["z1"], blk=blk: ops.wgrad(da1, z1, blk.c1.gw))
+                B.append(lambda da1=da1, z1=node["z1"], blk=blk: ops.wgrad(da1, z1, blk.c1.gw, max_ctas=wg_ctas))
                 dz1 = arena.get((nb, hh_, ww_, cin))
                 dgrad1x1(da1, blk.c1.wd, cin, dz1)
                 arena.put(da1)
@@ -802,12 +831,12 @@ class TrainEngine:
                 cat, up1, low3, y = node["cat"], node["up1"], node["low3"], node["y"]
                 gy = y.grad
                 h_ = cat.half
-                B.append(lambda gy=gy, cat=cat: ops.colstats(gy, cat.gb))
-                B.append(lambda gy=gy, cat=cat, u=up1.data, h_=h_: ops.wgrad(gy, u, cat.gw, co_valid=h_))
+                B.append(lambda gy=gy, cat=cat, s=scr(gy): ops.colstats(gy, cat.gb, scratch=s))
+                B.append(lambda gy=gy, cat=cat, u=up1.data, h_=h_: ops.wgrad(gy, u, cat.gw, co_valid=h_, max_ctas=wg_ctas))
                 dt = arena.get(low3.data.shape)
                 B.append(lambda gy=gy, dt=dt: ops.sumpool2x2(gy, dt, accumulate=False))
                 B.append(lambda dt=dt, cat=cat, l3=low3.data, h_=h_:
-                         ops.wgrad(dt, l3, cat.gw[h_ * cat.cig:], co_first=h_))
+                         ops.wgrad(dt, l3, cat.gw[h_ * cat.cig:], co_first=h_, max_ctas=wg_ctas))
                 assert up1.grad is None and low3.grad is None
                 up1.grad = arena.get(up1.data.shape)
                 dgrad1x1(gy, cat.wda, cat.cig, up1.grad)
@@ -825,8 +854,8 @@ class TrainEngine:
             elif kind == "remap":
                 rm, x, y2, y = node["rm"], node["x"], node["y2"], node["y"]
                 gy = y.grad
-                B.append(lambda gy=gy, rm=rm: ops.colstats(gy, rm.gbf_))
-                B.append(lambda gy=gy, rm=rm, y2=y2.data: ops.wgrad(gy, y2, rm.gwf_))
+                B.append(lambda gy=gy, rm=rm, s=scr(gy): ops.colstats(gy, rm.gbf_, scratch=s))
+                B.append(lambda gy=gy, rm=rm, y2=y2.data: ops.wgrad(gy, y2, rm.gwf_, max_ctas=wg_ctas))
                 assert y2.grad is None
                 y2.grad = arena.get(y2.data.shape)
                 dgrad1x1(gy, rm.wd, rm.ch, y2.grad)
@@ -839,8 +868,8 @@ class TrainEngine:
                 J = self.num_classes
                 dhp = arena.get((nb, hh_, ww_, 64))
                 B.append(lambda i=i, dhp=dhp: ops.nchw_to_nhwc_bf16_pad(plan.dheat[i], dhp))
-                B.append(lambda dhp=dhp, sc=sc, J=J: ops.colstats(dhp, sc.gb, c_valid=J))
-                B.append(lambda dhp=dhp, sc=sc, xd=x.data, J=J: ops.wgrad(dhp, xd, sc.gw, co_valid=J))
+                B.append(lambda dhp=dhp, sc=sc, J=J, s=scr(dhp): ops.colstats(dhp, sc.gb, c_valid=J, scratch=s))
+                B.append(lambda dhp=dhp, sc=sc, xd=x.data, J=J: ops.wgrad(dhp, xd, sc.gw, co_valid=J, max_ctas=wg_ctas))
                 if x.grad is None:
                     x.grad = arena.get(x.data.shape)
                     dgrad1x1(dhp, sc.wd, ch, x.grad)
@@ -852,7 +881,7 @@ class TrainEngine:
                 da = arena.get(y.data.shape)
                 bn_bwd(bn, y.grad, node["a"], da)
                 release(y)
-                B.append(lambda da=da, xd=x.data, cv=cv: ops.wgrad(da, xd, cv.gw))
+                B.append(lambda da=da, xd=x.data, cv=cv: ops.wgrad(da, xd, cv.gw, max_ctas=wg_ctas))
                 assert x.grad is None
                 x.grad = arena.get(x.data.shape)
                 dgrad1x1(da, cv.wd, cv.ci, x.grad)
@@ -863,7 +892,7 @@ class TrainEngine:
                 bn_bwd(self.stem_bn, y.grad, node["a0"], da0)
                 release(y)
                 B.append(lambda da0=da0, rows=node["rows"]: ops.wgrad(da0, rows, self.stem.gw, ci_valid=147, ld=147,
-                                                                      tap_stride=147))
+                                                                      tap_stride=147, max_ctas=wg_ctas))
                 arena.put(da0)
             else:
                 raise HgError(f"internal: unknown node kind {kind}")
@@ -924,18 +953,28 @@ class TrainEngine:
         self.steps += 1
         self.model._weights_epoch = getattr(self.model, "_weights_epoch", 0) + 1
 
+    def idle_step(self, lr: float, all_reduce: Optional[Callable] = None):
+        """A rank whose shard of a (ragged, last) batch is empty still takes part in the step's collective: zero
+        gradients in, the other ranks' sum out, the same RMSprop update as everywhere else."""
+        ops.zero_(self.store.G)
+        if all_reduce is not None:
+            all_reduce(self.store.G[:self.store.count])
+        self.rmsprop(lr)
+
     def train_step(self, x: torch.Tensor, target: torch.Tensor, target_weight: Optional[torch.Tensor], lr: float, *,
-                   use_graph: bool = True, world_size: int = 1, all_reduce: Optional[Callable] = None) -> torch.Tensor:
+                   use_graph: bool = True, world_size: int = 1, all_reduce: Optional[Callable] = None,
+                   grad_scale: Optional[float] = None) -> torch.Tensor:
         """One fused step: forward, JointsMSE loss, backward, (all-reduce,) RMSprop.  Returns the plan's loss
         tensor (device, fp32 [1]): the mean loss of THIS rank's shard; only the gradients carry the 1/world_size
-        factor, so that their sum over ranks is the gradient of the global-batch mean."""
+        factor (or `grad_scale` = shard size / global batch size when the shards are uneven), so that their sum over
+        ranks is the gradient of the global-batch mean."""
         n, _, h, w = x.shape
         plan = self.plan_for(n, h, w)
         plan.input.copy_(x, non_blocking=True)
         plan.target.copy_(target, non_blocking=True)
         if target_weight is not None:
             plan.target_weight.copy_(target_weight.reshape(n, -1), non_blocking=True)
-        gs = 1.0 / world_size
+        gs = 1.0 / world_size if grad_scale is None else float(grad_scale)
         if plan.grad_scale != gs or plan.use_target_weight != (target_weight is not None):
             plan.grad_scale, plan.use_target_weight = gs, target_weight is not None
             plan.graphs.clear()

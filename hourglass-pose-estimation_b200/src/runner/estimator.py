@@ -105,4 +105,7 @@ class Estimator:
             heatmaps = self.model(in_frame)[-1].detach()
         end = time.time()
         print(f"Inference time on {self.device}: %0.3f" % (end - start))
-        return self.post_process_heatmap_v2(heatmaps, (frame.shape[1], frame.shape[0]))
+        kps = self.post_process_heatmap_v2(heatmaps, (frame.shape[1], frame.shape[0]))
+        from hgb200.ops import check_err_word
+        check_err_word(self.device)              # the decode has synchronised: surface a kernel-side protocol timeout
+        return kps

@@ -4,6 +4,7 @@ import torch
 
 from src.loss.mse import MSELoss
 from src.utils.evaluation import AverageMeter, accuracy
+from hgb200.ops import check_err_word
 
 
 class Evaluator(object):
@@ -32,5 +33,6 @@ class Evaluator(object):
                 loss = self.criterion(outputs, heatmaps, target_weight)
                 acc = accuracy(last_hms, heatmaps, idxs, thr=self.cfg['COMMON']['pck'])
                 average_loss.update(loss.item(), images.size(0))
+                check_err_word(heatmaps.device)
                 average_acc.update(acc[0], images.size(0))
         return average_loss.avg, average_acc.avg

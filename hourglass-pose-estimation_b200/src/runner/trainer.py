@@ -5,8 +5,17 @@ GIL-bound replica threads, loss/optimizer on GPU 0) becomes ONE PROCESS PER GPU 
 runs the fused step (hgb200.train.TrainEngine.train_step) on its batch shard, BatchNorm uses the shard's
 statistics exactly as DataParallel replicas do, the flat gradient buffer is summed by ONE NCCL all-reduce
 over NVLink (the local loss is pre-scaled by 1/world so the sum is the global-batch mean), and RMSprop is a
-single fused launch over the flat parameter buffer.  Datasets are out of scope: the
-loaders are passed in; anything yielding (images, heatmaps, {'target_weight': ...}) works.
+single fused launch over the flat parameter buffer.
+
+Batches.  `cfg['TRAIN']['train_batch']` is the GLOBAL batch, as in the reference (DataParallel splits it over the
+GPUs): every rank sees the same sequence of global batches and trains on its contiguous shard of each
+(hgb200.shard.batch_shard), so the effective batch size and learning-rate regime do not change with the number of
+GPUs.  The gradient scale is shard size / global batch size, so uneven shards of a ragged last batch still sum to
+the global-batch mean, and a rank whose shard is empty still joins the all-reduce (TrainEngine.idle_step).
+Loaders: pass any iterables yielding (images, heatmaps, {'target_weight': ...}); with none passed they are built
+exactly as the reference builds them (trainer.py:47-58) from `src.datasets`, which re-exports the reference's
+dataset classes when a reference checkout is available (src/datasets/__init__.py) -- the shuffling generator is
+seeded identically on every rank so that all ranks draw the same global batches.
 """
 import os
 
@@ -16,6 +25,8 @@ import torch.distributed as dist
 from src.loss.mse import MSELoss
 from src import models
 from src.utils.evaluation import AverageMeter, accuracy
+from hgb200 import ops
+from hgb200.shard import batch_shard
 from hgb200.train import train_engine, RMSPROP_ALPHA, RMSPROP_EPS
 from hgb200.prefetch import DevicePrefetcher
 
@@ -118,9 +129,35 @@ class Trainer(object):
         self.best_acc = 0
         self.train_loader = train_loader
         self.val_loader = val_loader
+        if train_loader is None or val_loader is None:
+            self._build_loaders(train_loader is None, val_loader is None)
         self.idxs = cfg['MODEL']['subset']
         if os.path.isfile(cfg['COMMON'].get('resume', '') or ''):
             self._resume()
+
+    def _build_loaders(self, want_train, want_val):
+        """trainer.py:47-58: the reference's datasets and DataLoaders (global batches; same shuffle on every rank)."""
+        from src import datasets
+        import torch.utils.data
+        cfg = self.cfg
+        name = cfg['DATASET']['name']
+        if name not in datasets.__dict__:
+            raise KeyError(f"dataset '{name}' is not available: src.datasets re-exports the reference's dataset classes "
+                           f"from a reference checkout (HG_REFERENCE_SRC=<checkout>/src); pass train_loader / val_loader "
+                           f"otherwise")
+        seed = cfg.get('COMMON', {}).get('seed', 0)
+        if want_train:
+            train_dataset = datasets.__dict__[name](is_train=True, **cfg['DATASET'])
+            self.train_loader = torch.utils.data.DataLoader(
+                train_dataset, batch_size=cfg['TRAIN']['train_batch'], shuffle=True,
+                num_workers=cfg['TRAIN']['num_workers'], pin_memory=True,
+                generator=torch.Generator().manual_seed(seed))
+        if want_val:
+            val_dataset = datasets.__dict__[name](is_train=False, **cfg['DATASET'])
+            self.val_loader = torch.utils.data.DataLoader(
+                val_dataset, batch_size=cfg['TRAIN']['val_batch'], shuffle=True,
+                num_workers=cfg['TRAIN']['num_workers'], pin_memory=True,
+                generator=torch.Generator().manual_seed(seed + 1))
 
     # ------------------------------------------------------------------ checkpoints (reference format)
     def _resume(self):
@@ -144,32 +181,44 @@ class Trainer(object):
     def _all_reduce(self, flat_grads):
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
 
-    def train_step(self, images, heatmaps, target_weight):
-        """trainer.py:82-99 for one batch shard.  Returns (loss device tensor [1], last heat maps)."""
+    def train_step(self, images, heatmaps, target_weight, global_batch=None):
+        """trainer.py:82-99 for THIS rank's shard of a global batch of `global_batch` images (default: the shard is one
+        of `world` equal ones).  Returns (loss device tensor [1], last heat maps)."""
         lr = self.optimizer.param_groups[0]['lr']
+        n, _, h, w = images.shape
+        scale = n / float(global_batch) if global_batch else 1.0 / self.world
         loss = self.engine.train_step(images.to(self.device, non_blocking=True),
                                       heatmaps.to(self.device, non_blocking=True),
                                       target_weight.to(self.device, non_blocking=True), lr,
-                                      world_size=self.world,
+                                      world_size=self.world, grad_scale=scale,
                                       all_reduce=self._all_reduce if self.world > 1 else None)
-        n, _, h, w = images.shape
         return loss, self.engine.plans[(n, h, w)].outputs[-1]
 
     def _train_epoch(self):
         self.model.train()
         average_loss = AverageMeter()
         average_acc = AverageMeter()
+        sizes = []                       # global batch size of every step, in order (read when the shard arrives)
+
         def host_batches():
             for images, heatmaps, meta in self.train_loader:
                 if self.idxs:
                     heatmaps = torch.index_select(heatmaps, 1, torch.LongTensor(self.idxs))
-                yield images, heatmaps, meta['target_weight']
+                # this rank's contiguous shard of the global batch (the reference's DataParallel scatter, trainer.py:37)
+                lo, hi = batch_shard(images.size(0), self.world, self.rank)
+                sizes.append(images.size(0))
+                yield images[lo:hi], heatmaps[lo:hi], meta['target_weight'][lo:hi]
 
         # the batch of step i+1 crosses PCIe on a side stream while step i computes (hgb200/prefetch.py)
-        for images, heatmaps, target_weight in DevicePrefetcher(host_batches(), self.device):
-            loss, last_hms = self.train_step(images, heatmaps, target_weight)
+        for step, (images, heatmaps, target_weight) in enumerate(DevicePrefetcher(host_batches(), self.device)):
+            if images.size(0) == 0:      # fewer images than ranks in a ragged last batch: still join the collective
+                self.engine.idle_step(self.optimizer.param_groups[0]['lr'],
+                                      self._all_reduce if self.world > 1 else None)
+                continue
+            loss, last_hms = self.train_step(images, heatmaps, target_weight, global_batch=sizes[step])
             acc = accuracy(last_hms, heatmaps, self.idxs, thr=self.cfg['COMMON']['pck'])
             average_loss.update(loss.item(), images.size(0))
+            ops.check_err_word(self.device)          # the host has just synchronised: a kernel-side protocol timeout surfaces here
             average_acc.update(acc[0], images.size(0))
         return average_loss.avg, average_acc.avg
 
@@ -189,6 +238,7 @@ class Trainer(object):
                 loss = self.criterion(outputs, heatmaps, target_weight)
                 acc = accuracy(last_hms, heatmaps, self.idxs, thr=self.cfg['COMMON']['pck'])
                 average_loss.update(loss.item(), images.size(0))
+                ops.check_err_word(self.device)
                 average_acc.update(acc[0], images.size(0))
         is_best = False
         if average_acc.avg > self.best_acc:

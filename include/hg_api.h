@@ -33,7 +33,7 @@ extern "C" {
 #define HG_ERR_ARCH (-3)     /* device is not sm_100 */
 #define HG_ERR_DEVICE (-4)   /* a kernel reported a protocol timeout through its error word */
 
-#define HG_API_VERSION 7
+#define HG_API_VERSION 8
 
 int hg_api_version(void);
 /* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
@@ -222,16 +222,25 @@ int hg_jmse_loss(const float* const* preds, float* const* grads, const float* ta
  * taps == 1: off = 0.  taps == 9: both tensors are halo-padded buffers of identical geometry
  * (hg_conv3x3_halo_bf16) INCLUDING the leading zero row, rows = all positions, halo_pitch = w+1,
  * off(tap) = (tap/3-1)*halo_pitch + tap%3-1.   co <= 256 (multiple of 8), ci in {64,128,192,256}.
- * The pixel range is split over at most 36 CTAs (environment variable HG_WGRAD_CTAS overrides): the kernel is meant
- * to run beside other work of the backward pass. */
+ * The pixel range is split over at most max_ctas CTAs (0: the default of 36, or the environment variable HG_WGRAD_CTAS):
+ * the kernel is meant to run beside other work of the backward pass.  max_ctas = 1 disables the split, so that every
+ * element of dw is accumulated by one CTA in one fixed order (bit-reproducible; validation runs). */
 int hg_wgrad_bf16(const void* dout, const void* z, float* dw, unsigned int* err_word, int64_t rows, int32_t co,
                   int32_t co_first, int32_t co_valid, int32_t ci, int32_t ci_valid, int32_t taps, int32_t halo_pitch, int32_t ld,
-                  int32_t tap_stride, void* stream);
+                  int32_t tap_stride, int32_t max_ctas, void* stream);
 
 /* Per-channel sum (and sum of squares) over the pixels of an NHWC bf16 tensor, ADDED into fp32
  * accumulators (zeroed by the caller): batch statistics of nn.BatchNorm2d in train mode, and conv.bias.grad.
- * sumsq may be NULL; channels >= c_valid are skipped.  c in {64,128,256}. */
-int hg_colstats_nhwc(const void* x, float* sum, float* sumsq, int64_t pixels, int32_t c, int32_t c_valid, void* stream);
+ * sumsq may be NULL; channels >= c_valid are skipped.  c in {64,128,256}.
+ * shift != 0: the sums are taken about k[c] = x[pixel 0][c] -- sum (x-k) and sum (x-k)^2 -- so that the variance derived
+ * from them does not cancel when |mean| >> std (hg_bn_train_fwd with shifted != 0 undoes the shift).
+ * scratch == NULL: blocks add their partial sums with atomics (the fp32 additions happen in order of arrival).
+ * scratch != NULL (hg_colreduce_scratch_bytes(pixels, c) bytes of caller-owned device memory, zeroed ONCE before its first
+ * use, not shared between launches that may run concurrently): blocks park their partial sums there and the last one to
+ * arrive adds them in a fixed order -- bit-reproducible results whatever the scheduling. */
+int64_t hg_colreduce_scratch_bytes(int64_t pixels, int32_t c);
+int hg_colstats_nhwc(const void* x, float* sum, float* sumsq, int64_t pixels, int32_t c, int32_t c_valid, int32_t shift,
+                     float* scratch, void* stream);
 
 /* Train-mode BatchNorm2d (+ReLU) forward from batch sums (sums = [sum | sumsq], 2c floats):
  * out = [relu]((x - mean) * invstd * gamma + beta), biased variance, eps as given (torch: 1e-5).
@@ -241,14 +250,15 @@ int hg_colstats_nhwc(const void* x, float* sum, float* sumsq, int64_t pixels, in
  * is written).  Reference: the BatchNorm2d modules of src/models/modules.py:11-19 under model.train(). */
 int hg_bn_train_fwd(const void* x, const float* sums, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, int64_t* num_batches_tracked, float* saved, void* out, int32_t n, int32_t h,
-                    int32_t w, int32_t c, int32_t out_halo, int32_t relu, float eps, float momentum, void* stream);
+                    int32_t w, int32_t c, int32_t out_halo, int32_t relu, int32_t shifted, float eps, float momentum,
+                    void* stream);
 
 /* BatchNorm2d(+ReLU) backward.  Pass 1 adds s1 = sum dY and s2 = sum dY*xhat into sums (2c floats, zeroed by the
  * caller), dY = dz masked by the recomputed ReLU.  Pass 2 writes
  *   out = scale*(dY - s1/N - xhat*s2/N) [+ add1] [+ add2]       (bf16 NHWC, or halo-padded when out_halo)
  * and dgamma = s2, dbeta = s1 (fp32 [c], may both be NULL).  `out` may alias add1/add2 (element-wise in place). */
 int hg_bn_bwd_reduce(const void* dz, const void* x, const float* saved, float* sums, int64_t pixels, int32_t c,
-                     int32_t relu, void* stream);
+                     int32_t relu, float* scratch /* as hg_colstats_nhwc */, void* stream);
 int hg_bn_bwd_apply(const void* dz, const void* x, const float* saved, const float* sums, const void* add1,
                     const void* add2, void* out, float* dgamma, float* dbeta, int32_t n, int32_t h, int32_t w, int32_t c,
                     int32_t out_halo, int32_t relu, void* stream);

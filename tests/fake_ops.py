@@ -136,21 +136,29 @@ def nchw_to_nhwc_bf16_pad(x, out):
     return out
 
 
-def colstats(x, sum_out, sumsq_out=None, c_valid=None):
+def colreduce_scratch(pixels, c, device):
+    return torch.zeros(16, dtype=torch.float32, device=device)
+
+
+def colstats(x, sum_out, sumsq_out=None, c_valid=None, *, shift=False, scratch=None):
     c = x.shape[-1]
     cv = c if c_valid is None else c_valid
     xf = x.float().reshape(-1, c)
+    if shift:
+        xf = xf - xf[0]            # sums about x[pixel 0] (hg_colstats_nhwc)
     sum_out[:cv] += xf.sum(0)[:cv]
     if sumsq_out is not None:
         sumsq_out[:cv] += (xf * xf).sum(0)[:cv]
 
 
 def bn_train_fwd(x, sums, gamma, beta, running_mean, running_var, num_batches_tracked, saved, out, *, halo=False,
-                 relu=True, eps=1e-5, momentum=0.1):
+                 relu=True, eps=1e-5, momentum=0.1, shifted=False):
     n, h, w, c = x.shape
     N = n * h * w
     mean = sums[:c] / N
     var = (sums[c:2 * c] / N - mean * mean).clamp_min(0)
+    if shifted:
+        mean = mean + x.float().reshape(-1, c)[0]
     invstd = torch.rsqrt(var + eps)
     sc = gamma * invstd
     sh = beta - mean * sc
@@ -178,7 +186,7 @@ def _masked(dz, x, saved, relu):
     return dy, xhat
 
 
-def bn_bwd_reduce(dz, x, saved, sums, relu=True):
+def bn_bwd_reduce(dz, x, saved, sums, relu=True, scratch=None):
     c = x.shape[-1]
     dy, xhat = _masked(dz, x, saved, relu)
     sums[:c] += dy.reshape(-1, c).sum(0)
@@ -202,7 +210,8 @@ def bn_bwd_apply(dz, x, saved, sums, out, *, add1=None, add2=None, dgamma=None, 
     return out
 
 
-def wgrad(dout, z, dw, *, co_valid=None, co_first=0, ci_valid=None, taps=1, halo_pitch=0, ld=None, tap_stride=None):
+def wgrad(dout, z, dw, *, co_valid=None, co_first=0, ci_valid=None, taps=1, halo_pitch=0, ld=None, tap_stride=None,
+          max_ctas=0):
     co, ci = dout.shape[-1], z.shape[-1]
     cov = co if co_valid is None else co_valid
     civ = ci if ci_valid is None else ci_valid

@@ -38,7 +38,9 @@ def test_argument_validation_needs_no_device():
     assert lib.hg_dwconv3x3_nhwc(None, None, None, None, 1, 4, 4, 64, 0, 0, None) != 0
     assert lib.hg_preprocess_frames_u8(None, None, None, None, 1, 4, 4, 4, 4, None) != 0
     with pytest.raises(HgError):
-        lib.check(lib.hg_wgrad_bf16(None, None, None, None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, None), "hg_wgrad_bf16")
+        lib.check(lib.hg_wgrad_bf16(None, None, None, None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, None), "hg_wgrad_bf16")
+    assert lib.hg_colstats_nhwc(None, None, None, 0, 64, 64, 0, None, None) != 0
+    assert lib.hg_colreduce_scratch_bytes(0, 64) == 0 and lib.hg_colreduce_scratch_bytes(64, 48) == 0
 
 
 def test_product_path_fails_loudly_without_cuda():

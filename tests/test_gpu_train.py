@@ -104,18 +104,27 @@ def test_wgrad_3x3_halo(n, h, w, co, ci):
 @pytest.mark.parametrize("n,h,w,c,halo", [(2, 16, 16, 64, False), (2, 16, 16, 128, True), (3, 8, 8, 256, False),
                                           (2, 64, 48, 128, True), (5, 4, 4, 128, True), (1, 128, 128, 64, False),
                                           (32, 4, 4, 256, False)])
-def test_batchnorm_train_forward_backward(n, h, w, c, halo):
+@pytest.mark.parametrize("det", [False, True], ids=["atomic", "fixed_order"])
+def test_batchnorm_train_forward_backward(n, h, w, c, halo, det):
+    """det: the reductions run through per-launch scratch slots in a fixed order and the statistics are taken about
+    x[pixel 0] (hg_colstats_nhwc shift / scratch) -- the form the training plan uses."""
     from hgb200 import ops
     g = torch.Generator().manual_seed(c + h)
     x = (torch.randn(n, h, w, c, generator=g) * 1.5 + 0.3).to(torch.bfloat16).cuda()
+    scr = (lambda: ops.colreduce_scratch(n * h * w, c, "cuda")) if det else (lambda: None)
     gamma = (0.5 + torch.rand(c, generator=g)).cuda()
     beta = (0.2 * torch.randn(c, generator=g)).cuda()
     rm, rv = torch.zeros(c).cuda(), torch.ones(c).cuda()
     nbt = torch.zeros((), dtype=torch.int64).cuda()
     sums, saved = torch.zeros(2 * c).cuda(), torch.zeros(4 * c).cuda()
-    ops.colstats(x, sums[:c], sums[c:])
+    s1 = scr()
+    ops.colstats(x, sums[:c], sums[c:], shift=det, scratch=s1)
+    if det:                                                # the scratch is self-cleaning: a second use gives the same bits
+        again = torch.zeros(2 * c).cuda()
+        ops.colstats(x, again[:c], again[c:], shift=True, scratch=s1)
+        assert torch.equal(again, sums)
     out = ops.halo_padded_buffer(n, h, w, c, "cuda") if halo else torch.empty_like(x)
-    ops.bn_train_fwd(x, sums, gamma, beta, rm, rv, nbt, saved, out, halo=halo)
+    ops.bn_train_fwd(x, sums, gamma, beta, rm, rv, nbt, saved, out, halo=halo, shifted=det)
     xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     rm2, rv2 = torch.zeros(c).cuda(), torch.ones(c).cuda()
     gp, bp = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
@@ -126,7 +135,12 @@ def test_batchnorm_train_forward_backward(n, h, w, c, halo):
     dz = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).cuda()
     add1 = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).cuda()
     bs = torch.zeros(2 * c).cuda()
-    ops.bn_bwd_reduce(dz, x, saved, bs)
+    s2 = scr()
+    ops.bn_bwd_reduce(dz, x, saved, bs, scratch=s2)
+    if det:
+        again = torch.zeros(2 * c).cuda()
+        ops.bn_bwd_reduce(dz, x, saved, again, scratch=s2)
+        assert torch.equal(again, bs)
     dgam, dbet = torch.zeros(c).cuda(), torch.zeros(c).cuda()
     dx = ops.halo_padded_buffer(n, h, w, c, "cuda") if halo else torch.empty_like(x)
     ops.bn_bwd_apply(dz, x, saved, bs, dx, add1=None if halo else add1, dgamma=dgam, dbeta=dbet, halo=halo)
@@ -263,6 +277,29 @@ def test_pack_rmsprop_small_gemm_pad():
     out = torch.empty(2, 8, 6, 64, dtype=torch.bfloat16, device="cuda")
     ops.nchw_to_nhwc_bf16_pad(hm, out)
     assert torch.equal(out[..., :17].float(), r16(hm.permute(0, 2, 3, 1))) and float(out[..., 17:].abs().max()) == 0
+
+
+def test_shifted_statistics_survive_a_large_mean():
+    """|mean| >> std: E[x^2] - E[x]^2 in fp32 loses the variance; the sums about x[pixel 0] keep it."""
+    from hgb200 import ops
+    n, h, w, c = 8, 32, 32, 128
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randn(n, h, w, c, generator=g) * 0.25 + 200.0).to(torch.bfloat16).cuda()
+    xf = x.float().reshape(-1, c)
+    var_ref = xf.double().var(0, unbiased=False)
+    for shift, tol in ((True, 2e-3), (False, None)):
+        sums, saved = torch.zeros(2 * c).cuda(), torch.zeros(4 * c).cuda()
+        ops.colstats(x, sums[:c], sums[c:], shift=shift)
+        out = torch.empty_like(x)
+        ops.bn_train_fwd(x, sums, torch.ones(c).cuda(), torch.zeros(c).cuda(), None, None, None, saved, out, relu=False,
+                         shifted=shift)
+        var = 1.0 / saved[c:2 * c].double() ** 2 - 1e-5
+        err = float(((var - var_ref).abs() / var_ref).max())
+        if tol is not None:
+            assert err < tol, err
+            assert rel(saved[:c], xf.mean(0)) < 1e-6
+        else:
+            assert err > 0.05, "the unshifted form is expected to cancel here (if not, the shift is no longer needed)"
 
 
 # ------------------------------------------------------------------------------------------------ whole step
@@ -433,3 +470,38 @@ def test_training_needs_cuda_model():
     model = hg(num_stacks=1, num_blocks=1, num_classes=16, mobile=False, skip_mode="sum").train()
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 3, 64, 64))
+
+
+def _run_step_bits(tr, streams, x, tg, tw, S, J, monkeypatch):
+    monkeypatch.setattr(tr, "STREAMS", streams)
+    sd, model = _model(S, J)
+    eng = tr.TrainEngine(model)
+    out = []
+    for _ in range(2):                                               # two steps: the second starts from updated weights
+        loss = eng.train_step(x.cuda(), tg.cuda(), tw.cuda(), 2.5e-4)
+        torch.cuda.synchronize()
+        plan = eng.plans[(x.shape[0], x.shape[2], x.shape[3])]
+        out.append(dict(loss=float(loss), G=eng.store.G.clone(), P=eng.store.P.clone(), outs=[o.clone() for o in plan.outputs]))
+    tr.ops.check_err_word()
+    return out
+
+
+def test_deterministic_step_is_bit_reproducible_across_runs_and_streams(monkeypatch):
+    """HG_DETERMINISTIC (hgb200/train.py): fixed-order reductions make the step a pure function of its inputs, so a missing
+    dependency edge of the launch DAG or a read ahead of griddepcontrol.wait shows up as a BIT difference instead of hiding
+    in reduction noise.  Same step, twice on one stream and once as the 16-stream launch DAG: heat maps, the whole gradient
+    buffer and the updated parameters must be bit-identical (the loss scalar is one atomic sum: 1e-6)."""
+    import hgb200.train as tr
+    monkeypatch.setattr(tr, "DETERMINISTIC", True)
+    S, J, B, H, W = 2, 16, 4, 128, 128
+    x, tg, tw = train_inputs(1, B, J, H, W, 1)[0]
+    a = _run_step_bits(tr, 1, x, tg, tw, S, J, monkeypatch)
+    b = _run_step_bits(tr, 1, x, tg, tw, S, J, monkeypatch)
+    c = _run_step_bits(tr, 16, x, tg, tw, S, J, monkeypatch)
+    for name, other in (("second one-stream run", b), ("16-stream launch DAG", c)):
+        for step, (u, v) in enumerate(zip(a, other)):
+            for o1, o2 in zip(u["outs"], v["outs"]):
+                assert torch.equal(o1, o2), f"{name}, step {step}: heat maps differ"
+            assert torch.equal(u["G"], v["G"]), f"{name}, step {step}: gradients differ in {int((u['G'] != v['G']).sum())} elements"
+            assert torch.equal(u["P"], v["P"]), f"{name}, step {step}: parameters differ"
+            assert abs(u["loss"] - v["loss"]) <= 1e-6 * abs(u["loss"])

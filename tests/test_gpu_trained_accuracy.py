@@ -36,14 +36,28 @@ def synthetic_batch(n, gen, snap=False):
     return img, j3, torch.ones(n, J, 3, dtype=torch.float64)
 
 
-def test_trained_model_meets_the_accuracy_criteria():
+def _cosines(model, ref_grads):
+    rows = []
+    sdk = model.state_dict(keep_vars=True)
+    for k, gref in ref_grads.items():
+        gm = sdk[k].grad.detach().cpu().contiguous().reshape(-1).double()
+        gr = gref.reshape(-1).double()
+        rows.append((float((gm * gr).sum() / (gm.norm() * gr.norm() + 1e-300)), float(gr.norm()), k))
+    return rows
+
+
+def test_trained_model_meets_the_accuracy_criteria(monkeypatch):
+    import hgb200.train as tr
     from hgb200 import ops
-    from hgb200.train import train_engine
     from src.models import hg
     from src.utils.evaluation import accuracy
+    from oracle import train_oracle as T
+    # fixed-order reductions (hgb200/train.py: DETERMINISTIC): the 1000-step training run, and with it every figure below, is
+    # bit-reproducible from run to run instead of depending on the arrival order of fp32 atomics
+    monkeypatch.setattr(tr, "DETERMINISTIC", True)
     torch.manual_seed(0)
     model = hg(num_stacks=2, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum").cuda().train()
-    eng = train_engine(model)
+    eng = tr.train_engine(model)
     gen = torch.Generator().manual_seed(1)
     losses = []
     for step in range(STEPS):
@@ -55,6 +69,25 @@ def test_trained_model_meets_the_accuracy_criteria():
             losses.append(float(loss))
     ops.check_err_word()
     assert losses[-1] < 0.35 * losses[0], losses               # the sm_100a training path learns the task
+    # ---- gradients at the TRAINED state (where train-mode BatchNorm no longer amplifies rounding noise chaotically, as it
+    #      does at random initialisation): one more step, every parameter tensor's gradient against the fp32 training oracle
+    #      on the same weights and batch: cosine >= 0.99
+    sd0 = {k: v.detach().cpu().clone().contiguous() for k, v in model.state_dict().items()}
+    img, joints, vis = synthetic_batch(16, gen)
+    mu, wt = ops.joint_centers(joints.cuda(), vis.cuda(), (W // 4, H // 4), (W, H), 1)
+    tgt = ops.gaussian_target(mu, wt, (W // 4, H // 4), 1)
+    loss_gpu = float(eng.train_step(img.cuda(), tgt, wt, 2.5e-4))
+    ref_loss, _, ref_grads = T.forward_backward(sd0, img, tgt.cpu(), wt.cpu().reshape(16, J, 1))
+    assert abs(loss_gpu - ref_loss) <= 2e-2 * ref_loss, (loss_gpu, ref_loss)
+    rows = _cosines(model, ref_grads)
+    gmax = max(r[1] for r in rows)
+    sig = [r for r in rows if r[1] > 1e-3 * gmax]              # tensors whose gradient is not numerically nil
+    worst = sorted(sig)[:5]
+    grad_report = (f"gradient cosine vs fp32 oracle at the trained state: min {worst[0][0]:.4f}, median "
+                   f"{np.median([r[0] for r in sig]):.4f} over {len(sig)} tensors; worst: "
+                   + ", ".join(f"{k} {c:.4f}" for c, _, k in worst))
+    print("\n" + grad_report)
+    assert worst[0][0] >= 0.99, grad_report
     # ---- held-out evaluation: reference arithmetic (fp32 oracle, CPU) against the bf16 engine
     model.eval()
     sd = {k: v.detach().cpu().contiguous() for k, v in model.state_dict().items()}
@@ -86,10 +119,19 @@ def test_trained_model_meets_the_accuracy_criteria():
             assert float(rf[i, a_ref[i]] - rf[i, a_mine[i]]) <= 2 * err * peak + 1e-6
         assert acc_ref[0] > 0.6, acc_ref                                     # the trained model localises the blobs
         assert abs(acc_mine[0] - acc_ref[0]) <= 0.002 + 1e-9, (acc_mine[0], acc_ref[0])   # PCK@0.5 within 0.2 points
-        # Identical arg-max: the north star asks for >= 99.5 %.  On this 1000-step toy model the figure depends on the
-        # (chaotic) training run -- 98.5 % to 99.9 % over fourteen trainings, for blobs on pixel centres as well as at
-        # continuous positions -- because 0.1-1.5 % of its maps have two neighbouring pixels within 2e-2 of each other, where
-        # the reference's own arg-max is decided inside the stated heat-map tolerance.  The floor asserted here leaves a
-        # margin under every run seen; the per-run figures are printed and archived (profiles/r1_trained_accuracy.log).
-        assert same >= 0.97, same
-    print("\nlosses", losses, *report, sep="\n")
+        # Identical arg-max, north star: >= 99.5 %.  Two maps that agree within the heat-map tolerance (2e-2 of the peak) can
+        # only be REQUIRED to share their arg-max where the reference's own decision clears that tolerance: maps whose best
+        # and second-best DISTINCT-pixel values lie within 2 x (measured max error) of each other are near-ties of the
+        # reference itself (blobs half-way between two heat-map pixels).  Asserted: raw agreement >= 99.5 % for blobs on pixel
+        # centres (the well-conditioned case); for blobs at continuous positions >= 99.5 % of the maps that clear the band
+        # (and the raw figure is printed and bounded below).
+        top2 = rf.topk(2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 2 * err * peak
+        same_clear = float((a_ref == a_mine)[clear].float().mean())
+        report.append(f"    maps clearing the tolerance band: {int(clear.sum())} of {N_EVAL * J}, agreement on them {same_clear:.4f}")
+        assert same_clear >= 0.995, same_clear
+        if snap:
+            assert same >= 0.995, same
+        else:
+            assert same >= 0.985, same
+    print("\nlosses", losses, grad_report, *report, sep="\n")
