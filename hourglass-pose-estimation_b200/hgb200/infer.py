@@ -13,6 +13,8 @@ from typing import Iterable, Iterator, Optional, Tuple
 import numpy as np
 import torch
 
+from . import ops as _ops
+from ._lib import HgError
 from .engine import HourglassEngine, Plan
 from .flip import MPII_FLIP_PAIRS
 
@@ -30,6 +32,14 @@ class FlipTestPipeline:
         self._stage = [torch.empty_like(self.plan.input) for _ in range(2)]
         self._ready = [torch.cuda.Event() for _ in range(2)]
         self._consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def _check(self, err_host: torch.Tensor):
+        """The device error word rides back with every batch's coordinates (no extra synchronisation): a kernel-side
+        protocol timeout raises here instead of handing out garbage coordinates."""
+        v = int(err_host[0])
+        if v != 0:
+            _ops.err_word(self.device).zero_()
+            raise HgError(f"device-side protocol timeout, code 0x{v & 0xffffffff:x} (role<<8 | barrier)")
 
     @property
     def launches_per_batch(self) -> int:
@@ -55,6 +65,8 @@ class FlipTestPipeline:
             self._stage_u8 = [torch.empty((self.batch, self.h, self.w, 3), dtype=torch.uint8, device=self.device)
                               for _ in range(2)]
         out_host = [torch.empty(self.plan.coords.shape, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        err_host = [torch.zeros(1, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        err_dev = _ops.err_word(self.device)
         for s in range(2):
             self._consumed[s].record(main)
         pending = None
@@ -69,15 +81,18 @@ class FlipTestPipeline:
             self._consumed[slot].record(main)
             self.plan.run()
             out_host[slot].copy_(self.plan.coords, non_blocking=True)
+            err_host[slot].copy_(err_dev, non_blocking=True)
             done = torch.cuda.Event()
             done.record(main)
             if pending is not None:
                 pending[0].synchronize()
+                self._check(pending[2])
                 yield pending[1].numpy().copy()
-            pending = (done, out_host[slot])
+            pending = (done, out_host[slot], err_host[slot])
             slot ^= 1
         if pending is not None:
             pending[0].synchronize()
+            self._check(pending[2])
             yield pending[1].numpy().copy()
 
     def infer_host(self, batches: Iterable[torch.Tensor]) -> Iterator[np.ndarray]:
@@ -88,6 +103,8 @@ class FlipTestPipeline:
         slot = 0
         pending = None
         out_host = [torch.empty(self.plan.coords.shape, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        err_host = [torch.zeros(1, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        err_dev = _ops.err_word(self.device)
 
         def stage(xh, s):
             with torch.cuda.stream(self.copy_stream):
@@ -110,13 +127,16 @@ class FlipTestPipeline:
             self._consumed[cur_slot].record(main)
             self.plan.run()
             out_host[cur_slot].copy_(self.plan.coords, non_blocking=True)
+            err_host[cur_slot].copy_(err_dev, non_blocking=True)
             done = torch.cuda.Event()
             done.record(main)
             if pending is not None:
                 pending[0].synchronize()
+                self._check(pending[2])
                 yield pending[1].numpy().copy()
-            pending = (done, out_host[cur_slot])
+            pending = (done, out_host[cur_slot], err_host[cur_slot])
             slot ^= 1
         if pending is not None:
             pending[0].synchronize()
+            self._check(pending[2])
             yield pending[1].numpy().copy()

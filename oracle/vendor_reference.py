@@ -2,8 +2,9 @@
 not exist (the GPU box).  Test / baseline infrastructure only (see oracle/__init__.py).
 
 The reference is pure Python with no build or install metadata (no setup.py / pyproject), so "building" it is a byte copy
-of the files the path needs -- `src/__init__.py`, `src/models/*`, `src/loss/*`, `src/utils/*` -- from where they lie under
-/root/reference into `oracle/_ref/src/`, plus a MANIFEST.json with each file's sha256.  `oracle/_ref/` is git-ignored (no
+of the files the path needs -- `src/__init__.py`, `src/models/*`, `src/loss/*`, `src/utils/*`, and the entry script
+`scripts/estimate.py` whose flow tests/test_gpu_dropin.py executes against this repo's `src` -- from where they lie under
+/root/reference into `oracle/_ref/`, plus a MANIFEST.json with each file's sha256.  `oracle/_ref/` is git-ignored (no
 reference source enters the history) but travels with `gpurun`.  `__graft_entry__.build()` runs this when /root/reference
 is present; `bench.py --impl reference` and the `gpu_baseline` leg import the copy (`kind: "reference"`) and fall back to
 the oracle port (`kind: "port"`) when it is absent.
@@ -21,6 +22,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEST = os.path.join(HERE, "_ref")
 PARTS = ("__init__.py", "models", "loss", "utils")
+SCRIPTS = ("scripts/estimate.py",)
 
 
 def vendor(reference_root: str = "/root/reference") -> bool:
@@ -36,6 +38,14 @@ def vendor(reference_root: str = "/root/reference") -> bool:
         files = [p] if os.path.isfile(p) else [os.path.join(p, f) for f in sorted(os.listdir(p)) if f.endswith(".py")]
         for f in files:
             rel = os.path.relpath(f, reference_root)
+            out = os.path.join(DEST, rel)
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            shutil.copyfile(f, out)
+            with open(f, "rb") as fh:
+                manifest[rel] = hashlib.sha256(fh.read()).hexdigest()
+    for rel in SCRIPTS:
+        f = os.path.join(reference_root, rel)
+        if os.path.isfile(f):
             out = os.path.join(DEST, rel)
             os.makedirs(os.path.dirname(out), exist_ok=True)
             shutil.copyfile(f, out)

@@ -136,3 +136,67 @@ def test_device_prefetcher_and_lagged_scalar():
     want = [i + 100.0 * i for i in range(9)]
     assert [float(s) for s in seen] == want
     assert lagged == want
+
+
+# ------------------------------------------------------------------------------------------------ stand-alone modules
+def test_standalone_bottleneck_and_hourglass_modules_match_the_oracle():
+    """modules.py:27-47 and :80-99 called on their own (eval mode): same kernels as the network plan, fp32 oracle as
+    the yardstick (bf16 storage: 2e-2 of the peak)."""
+    from src.models.modules import HGBottleneck, Hourglass
+    from oracle.hourglass_oracle import bottleneck, hourglass
+    torch.manual_seed(3)
+    for mobile, skip in ((False, "sum"), (True, "concat")):
+        blk = HGBottleneck(256, 128, mobile=mobile).cuda().eval()
+        hgm = Hourglass(HGBottleneck, 1, 128, 4, mobile, skip_mode=skip).cuda().eval()
+        with torch.no_grad():
+            for m in list(blk.modules()) + list(hgm.modules()):
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.running_mean.normal_(0, 0.1)
+                    m.running_var.uniform_(0.5, 1.5)
+                    m.weight.uniform_(0.75, 1.25)
+                    m.bias.normal_(0, 0.1)
+        x = torch.randn(2, 256, 32, 32, generator=torch.Generator().manual_seed(4))
+        with torch.no_grad():
+            got = blk(x.cuda()).cpu()
+            ref = bottleneck({"b." + k: v.cpu() for k, v in blk.state_dict().items()}, "b", x)
+            assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
+            got = hgm(x.cuda()).cpu()
+            ref = hourglass({"m." + k: v.cpu() for k, v in hgm.state_dict().items()}, "m", 4, x)
+            assert got.shape == ref.shape
+            assert float((got - ref).abs().max()) <= 2e-2 * float(ref.abs().max()), (mobile, skip)
+    blk.train()
+    with pytest.raises(RuntimeError):
+        blk(x.cuda())
+
+
+# ------------------------------------------------------------------------------------------------ the reference's own script
+def test_reference_estimate_script_runs_unmodified_over_this_src(tmp_path, monkeypatch, capsys):
+    """scripts/estimate.py:7-24 of the reference, byte for byte (vendored into oracle/_ref by oracle/vendor_reference.py),
+    executed with THIS repo's `src` package on the path: yaml config -> Estimator(cfg) -> checkpoint in the reference's
+    format -> cv2.imread -> estimator.run(frame) -> circles drawn -> cv2.imwrite."""
+    import runpy
+    import sys
+    import cv2
+    import yaml
+    from oracle.vendor_reference import verify, DEST
+    from oracle.hourglass_oracle import make_state_dict
+    script = os.path.join(DEST, "scripts", "estimate.py")
+    if not (verify() and os.path.isfile(script)):
+        pytest.skip("oracle/_ref is not vendored in this checkout (python oracle/vendor_reference.py)")
+    sd = make_state_dict(num_stacks=2, num_blocks=1, num_classes=17, mobile=True, skip_mode="sum", seed=5)
+    ckpt = tmp_path / "checkpoint.pth.tar"
+    torch.save({"epoch": 1, "best_acc": 0.0, "state_dict": {"module." + k: v for k, v in sd.items()}}, str(ckpt))
+    frame = np.random.RandomState(0).randint(0, 256, (240, 320, 3), dtype=np.uint8)
+    img, dest = tmp_path / "in.png", tmp_path / "out.png"
+    cv2.imwrite(str(img), frame)
+    cfg = {"MODEL": {"arch": "hg", "num_stacks": 2, "mobile": True, "skip_mode": "sum", "num_classes": 17, "subset": None},
+           "COMMON": {"gpu": os.environ.get("CUDA_VISIBLE_DEVICES", "0"), "image_path": str(img), "dest_path": str(dest),
+                      "out_res": 64, "in_res": 256, "dataset": "mscoco", "resume": str(ckpt)}}
+    cfg_path = tmp_path / "inference.yaml"
+    cfg_path.write_text(yaml.safe_dump(cfg))
+    monkeypatch.setattr(sys, "argv", [script, str(cfg_path)])
+    runpy.run_path(script, run_name="__main__")
+    out = capsys.readouterr().out
+    assert "creating model 'hg', stacks=2" in out and "Inference time on cuda" in out
+    drawn = cv2.imread(str(dest))
+    assert drawn is not None and drawn.shape == frame.shape and (drawn != frame).any()      # the key points were drawn
