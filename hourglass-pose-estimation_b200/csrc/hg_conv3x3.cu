@@ -567,14 +567,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) conv3x3_pair
 // same warps then add bias, the residual and optionally the nearest-upsampled low-resolution tensor (both read from
 // global memory at the pixel's dense position) and store the 256-channel result.  Order on the tensor pipe:
 // K2(t), K3(t-1), K2(t+1), ... so the epilogue of tile t overlaps K2(t+1).
-// Warps: 0 A producer, 1 MMA issuer (+TMEM), 2 B producer, 3 W3 loader, 4..11 epilogue (two per TMEM lane quarter: the
-// lower four take the low half of the columns, the upper four the high half).
+// Warps: 0 A producer, 1 MMA issuer (+TMEM), 2 B producer, 3 W3 loader, 4..11 K3 drain (two per TMEM lane quarter: the
+// lower four take the low half of the columns, the upper four the high half), 12..15 K2 drain (one per lane quarter).
+// The two drains run on separate warps: the K3 drain is the long pole of a tile (global loads and stores), and with the K2
+// drain ahead of it in the same warps it also paid that drain, the wait for the single operand buffer and a cluster-scope
+// release behind its own output stores -- 37 % of the epilogue's time (profiles/r2_ncu_k3_fused_epilogue.txt).
 // ================================================================================================================
 constexpr int kSlab16 = 128 * kBlockK * 2;              // [128 rows x 64 k] bf16, 128-byte swizzled
 
 // kRes / kUp: residual / upsample operand present (separate instantiations: no runtime predicates in the issue-bound epilogue)
 template <bool kRes, bool kUp>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_pair_kernel(const __grid_constant__ Params p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) conv3x3_k3_pair_kernel(const __grid_constant__ Params p) {
     constexpr int BLOCK_N = 128;
     constexpr int kTmemCols = 512;                      // K2: 2 x 128 at [0,256); K3: 256 at [256,512)
     constexpr uint32_t kAcc3 = 256;
@@ -594,8 +597,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
     uint64_t* b_full = bars + 4;              // [kPairBStages] (leader)
     uint64_t* b_empty = b_full + kPairBStages;
     uint64_t* tmem_full_bar = b_empty + kPairBStages;   // [2]
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]   (leader; 8 epilogue warps of each CTA)
-    uint64_t* a2_full = tmem_empty_bar + 2;             // (leader; 16 warps)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;       // [2]   (leader; 4 K2 drain warps of each CTA)
+    uint64_t* a2_full = tmem_empty_bar + 2;             // (leader; 8 warps)
     uint64_t* a2_empty = a2_full + 1;
     uint64_t* acc3_full = a2_empty + 1;
     uint64_t* acc3_empty = acc3_full + 1;               // (leader; 16 warps)
@@ -617,13 +620,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
             mbar_init(&a_full[s], 1);
             mbar_init(&a_empty[s], 1);
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 16);
+            mbar_init(&tmem_empty_bar[s], 8);
         }
         for (int s = 0; s < kPairBStages; ++s) {
             mbar_init(&b_full[s], 1);
             mbar_init(&b_empty[s], 1);
         }
-        mbar_init(a2_full, 16);
+        mbar_init(a2_full, 8);
         mbar_init(a2_empty, 1);
         mbar_init(acc3_full, 1);
         mbar_init(acc3_empty, 16);
@@ -755,21 +758,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
             }
             if (ok && it > 0) issue_k3(it - 1);
         }
+    } else if (warp_idx >= 12) {
+        // ===================== K2 drain warps: 3x3 accumulators -> bias + ReLU (folded bn3) -> bf16 K3 operand =====================
+        // One warp per TMEM lane quarter, all 128 columns.  These warps never touch global memory, so the cluster-scope RELEASE
+        // that hands the operand to the leader's MMA thread has nothing to wait for (in the K3 drain warps the same arrive sat
+        // behind the previous tile's output stores: MEMBAR/ERRBAR, a fifth of the epilogue's time in the ncu source page).
+        const int q = warp_idx & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t a2_row = smem_u32(smem_a2) + row * 128;
+        const uint32_t bias2_s = smem_u32(s_bias2);
+        int it = 0;
+        bool ok = true;
+        for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs, ++it) {
+            const int acc = it & 1;
+            ok = mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1u, p.err_word, 0x3c01);
+            if (!ok) break;
+            ok = mbar_wait(a2_empty, static_cast<uint32_t>(it & 1) ^ 1u, p.err_word, 0x3c02);   // K3(it-1) has read the operand buffer
+            if (!ok) break;
+            tc_fence_after();
+#pragma unroll
+            for (int slab = 0; slab < 2; ++slab) {
+                uint32_t v0[32], v1[32];
+                const uint32_t t2 = lane_base + static_cast<uint32_t>(acc * BLOCK_N + slab * 64);
+                tmem_ld_32x32(t2, v0);
+                tmem_ld_32x32(t2 + 32, v1);
+                tmem_ld_wait();
+                if (slab == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_on_leader_relaxed(&tmem_empty_bar[acc]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t* vv = j < 4 ? &v0[j * 8] : &v1[(j - 4) * 8];
+                    const uint32_t bs = bias2_s + static_cast<uint32_t>((slab * 64 + j * 8) * 4);
+                    const float4 ba = lds128f(bs), bb = lds128f(bs + 16);
+                    const unsigned long long a0 = f2_add(f2_pack(__uint_as_float(vv[0]), __uint_as_float(vv[1])), f2_pack(ba.x, ba.y));
+                    const unsigned long long a1 = f2_add(f2_pack(__uint_as_float(vv[2]), __uint_as_float(vv[3])), f2_pack(ba.z, ba.w));
+                    const unsigned long long a2 = f2_add(f2_pack(__uint_as_float(vv[4]), __uint_as_float(vv[5])), f2_pack(bb.x, bb.y));
+                    const unsigned long long a3 = f2_add(f2_pack(__uint_as_float(vv[6]), __uint_as_float(vv[7])), f2_pack(bb.z, bb.w));
+                    uint4 w4;
+                    w4.x = pack_bf16x2_relu(f2_lo(a0), f2_hi(a0));
+                    w4.y = pack_bf16x2_relu(f2_lo(a1), f2_hi(a1));
+                    w4.z = pack_bf16x2_relu(f2_lo(a2), f2_hi(a2));
+                    w4.w = pack_bf16x2_relu(f2_lo(a3), f2_hi(a3));
+                    sts128(a2_row + slab * kSlab16 + ((j ^ (row & 7)) << 4), w4);
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_on_leader(a2_full);
+        }
     } else if (warp_idx >= 4) {
-        // ===================== epilogue warps: K2 accumulators -> K3 operand, K3 accumulators -> output =====================
+        // ===================== K3 drain warps: 1x1 accumulators + bias + residual (+ upsampled) -> output =====================
         pdl_wait();
         const int q = warp_idx & 3;
         const int ch = (warp_idx - 4) >> 2;                 // column half this warp owns
         const int row = q * 32 + lane;
         const long long img_pos = static_cast<long long>(p.H + 1) * p.P;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const uint32_t a2_row = smem_u32(smem_a2) + ch * kSlab16 + row * 128;
-        long long prev_low = 0;
-        int prev_px = -1;                                    // dense pixel index of this lane's row in the tile being drained
+        long long cur_low = 0;
+        int cur_px = -1;                                     // dense pixel index of this lane's row in the tile being drained
         // warp-private staging: 2 buffers of [32 rows x 32 channels] bf16 (64-byte rows, 16-byte chunks swizzled so that both
         // the row-per-lane and the four-lanes-per-row access patterns are bank-conflict free); no CTA-level barriers
         const uint32_t wstage = smem_u32(smem_stage) + static_cast<uint32_t>(warp_idx - 4) * 4096u;
-        const uint32_t bias3_s = smem_u32(s_bias3), bias2_s = smem_u32(s_bias2);
+        const uint32_t bias3_s = smem_u32(s_bias3);
         auto sw = [](int r, int chunk) -> uint32_t { return static_cast<uint32_t>(r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4)); };
         int it = 0;
         bool ok = true;
@@ -791,12 +845,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        // where the rows of `tile` live in the dense tensors
+        auto locate = [&](int tile) {
+            const long long f = static_cast<long long>(tile) * kBM + rank * 128 + row;
+            const long long n = f / img_pos;
+            const int r = static_cast<int>(f - n * img_pos);
+            const int y = r / p.P, x = r - y * p.P;
+            const bool valid = (f < p.total_pos) && (x < p.W) && (y < p.H);
+            cur_px = valid ? static_cast<int>((n * p.H + y) * p.W + x) : -1;
+            cur_low = (n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int px = __shfl_sync(0xffffffffu, cur_px, k * 8 + (lane >> 2));
+                mv_off[k] = px >= 0 ? static_cast<long long>(px) * 256 + ch * 128 + (lane & 3) * 8 : -1;
+            }
+        };
 
         auto drain_k3 = [&](int j) -> bool {
             // tile j's 1x1 result, 32 channels at a time: the residual waits in the warp's staging buffer, each lane adds its
             // row in place, and the sub-slab leaves with 64 contiguous bytes per row (eight rows per store instruction)
-            const bool valid = prev_px >= 0;
-            const __nv_bfloat16* u = kUp ? p.up + prev_low * 256 + ch * 128 : nullptr;
+            const bool valid = cur_px >= 0;
+            const __nv_bfloat16* u = kUp ? p.up + cur_low * 256 + ch * 128 : nullptr;
             uint32_t ur2[2][16];                             // upsample operand, one phase ahead
             if (kUp && valid) {
                 ldg_nc_v8(u, ur2[0]);
@@ -861,67 +930,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1) conv3x3_k3_p
             return true;
         };
 
-        for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs, ++it) {
-            const int acc = it & 1;
-            ok = mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1u, p.err_word, 0x3c01);
-            if (!ok) break;
-            ok = mbar_wait(a2_empty, static_cast<uint32_t>(it & 1) ^ 1u, p.err_word, 0x3c02);   // K3(it-1) has read the operand buffer
-            if (!ok) break;
-            tc_fence_after();
-            {
-                uint32_t v0[32], v1[32];
-                const uint32_t t2 = lane_base + static_cast<uint32_t>(acc * BLOCK_N + ch * 64);
-                tmem_ld_32x32(t2, v0);
-                tmem_ld_32x32(t2 + 32, v1);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_on_leader_relaxed(&tmem_empty_bar[acc]);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t* vv = j < 4 ? &v0[j * 8] : &v1[(j - 4) * 8];
-                    const uint32_t bs = bias2_s + static_cast<uint32_t>((ch * 64 + j * 8) * 4);
-                    const float4 ba = lds128f(bs), bb = lds128f(bs + 16);
-                    const unsigned long long a0 = f2_add(f2_pack(__uint_as_float(vv[0]), __uint_as_float(vv[1])), f2_pack(ba.x, ba.y));
-                    const unsigned long long a1 = f2_add(f2_pack(__uint_as_float(vv[2]), __uint_as_float(vv[3])), f2_pack(ba.z, ba.w));
-                    const unsigned long long a2 = f2_add(f2_pack(__uint_as_float(vv[4]), __uint_as_float(vv[5])), f2_pack(bb.x, bb.y));
-                    const unsigned long long a3 = f2_add(f2_pack(__uint_as_float(vv[6]), __uint_as_float(vv[7])), f2_pack(bb.z, bb.w));
-                    uint4 w4;
-                    w4.x = pack_bf16x2_relu(f2_lo(a0), f2_hi(a0));
-                    w4.y = pack_bf16x2_relu(f2_lo(a1), f2_hi(a1));
-                    w4.z = pack_bf16x2_relu(f2_lo(a2), f2_hi(a2));
-                    w4.w = pack_bf16x2_relu(f2_lo(a3), f2_hi(a3));
-                    sts128(a2_row + ((j ^ (row & 7)) << 4), w4);
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_on_leader(a2_full);
-            }
-            if (it > 0) {
-                ok = drain_k3(it - 1);
-                if (!ok) break;
-            }
-            // where this tile's row lives in the dense tensors (used when ITS 1x1 result is drained, one iteration later)
-            const long long f = static_cast<long long>(tile) * kBM + rank * 128 + row;
-            const long long n = f / img_pos;
-            const int r = static_cast<int>(f - n * img_pos);
-            const int y = r / p.P, x = r - y * p.P;
-            const bool valid = (f < p.total_pos) && (x < p.W) && (y < p.H);
-            prev_px = valid ? static_cast<int>((n * p.H + y) * p.W + x) : -1;
-            prev_low = (n * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int px = __shfl_sync(0xffffffffu, prev_px, k * 8 + (lane >> 2));
-                mv_off[k] = px >= 0 ? static_cast<long long>(px) * 256 + ch * 128 + (lane & 3) * 8 : -1;
-            }
-            // the first two residual sub-slabs of THIS tile (drained one iteration later) fly while the next tile's 3x3 runs.
-            // Issued here, not before the operand hand-over above: that arrive is a RELEASE, and a release by a thread with
-            // cp.async or global stores in flight waits for them (MEMBAR) on the tensor pipe's critical path.
-            __syncwarp();                                    // every lane has read the staging buffers of the tile just drained
+        if (pair < p.num_tiles) {
+            locate(pair);
             fetch_res(0);
             fetch_res(1);
         }
-        if (ok && it > 0) drain_k3(it - 1);
+        for (int tile = pair; tile < p.num_tiles && ok; tile += num_pairs, ++it) {
+            ok = drain_k3(it);
+            if (!ok) break;
+            // the first two residual sub-slabs of the NEXT tile fly while its 3x3 and 1x1 run
+            if (tile + num_pairs < p.num_tiles) {
+                locate(tile + num_pairs);
+                __syncwarp();                                // every lane has read the staging buffers of the tile just drained
+                fetch_res(0);
+                fetch_res(1);
+            }
+        }
     }
 
     tc_fence_before();
@@ -1185,6 +1209,6 @@ extern "C" int hg_conv3x3_k3_fused_bf16(const void* in_padded, const void* w2, c
     }
     const int smem_bytes = 1024 + 2 * kp.region_bytes + kp.b_stages * kPairBStage + 6 * kSlab16 + (128 + 256 + 256) * 4 + 1024;
     const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-    HG_CUDA_OK(launch_kernel(kern, dim3(2 * pairs), dim3(384), smem_bytes, static_cast<cudaStream_t>(stream), kp));
+    HG_CUDA_OK(launch_kernel(kern, dim3(2 * pairs), dim3(512), smem_bytes, static_cast<cudaStream_t>(stream), kp));
     return HG_OK;
 }
