@@ -649,20 +649,15 @@ def bench_train(ctx: Ctx, args):
     vis = (rng.rand(B, J, 1) < 0.8).astype(np.float64).repeat(3, 2)
     host_j, host_v = torch.from_numpy(joints).pin_memory(), torch.from_numpy(vis).pin_memory()
     x_dev, j_dev, v_dev = host_x[0].to(device), host_j.to(device), host_v.to(device)
-    ar_events = []
-
     def reduce_fn(flat):
-        """The step's one exchange: NCCL all-reduce (sum) of the flat fp32 gradient buffer, bracketed by CUDA events."""
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        """The step's exchange: NCCL all-reduce (sum) of a slice of the flat fp32 gradient buffer.  hgb200.train issues it
+        per bucket INSIDE the step's CUDA graph, on its own stream, behind the last weight-gradient launch of the bucket."""
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        b.record()
-        ar_events.append((a, b))
 
-    def step(x, jt, vs):
+    def step(x, jt, vs, exchange=True):
         mu, wt = ops.joint_centers(jt, vs, (W // 4, H // 4), (W, H), 1)          # on-device Gaussian targets (A7)
         tgt = ops.gaussian_target(mu, wt, (W // 4, H // 4), 1)
-        return eng.train_step(x, tgt, wt, lr, world_size=world, all_reduce=reduce_fn if world > 1 else None)
+        return eng.train_step(x, tgt, wt, lr, world_size=world, all_reduce=reduce_fn if (world > 1 and exchange) else None)
 
     for _ in range(warmup):
         loss = step(x_dev, j_dev, v_dev)
@@ -681,7 +676,6 @@ def bench_train(ctx: Ctx, args):
             torch.cuda.synchronize(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.barrier()
-    ar_events.clear()
     e0.record()
     for _ in range(steps):
         loss = step(x_dev, j_dev, v_dev)
@@ -689,7 +683,6 @@ def bench_train(ctx: Ctx, args):
     ctx.barrier()
     clocks = sampler.stop() if sampler else None
     ms_step = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
-    allreduce_ms = ctx.max_over_ranks(sum(a.elapsed_time(b) for a, b in ar_events) / max(len(ar_events), 1)) if world > 1 else 0.0
     value = world * B / (ms_step * 1e-3)
     ops.check_err_word(device)
     loss1 = float(loss)
@@ -706,6 +699,32 @@ def bench_train(ctx: Ctx, args):
     torch.cuda.synchronize(device)
     e2e_value = world * B * steps / ctx.max_over_ranks(time.perf_counter() - t0)
     ops.check_err_word(device)
+    # ---- the exchange by itself, and what of it the step still sees (N > 1): (a) the whole flat buffer all-reduced
+    #      eagerly, alone on the GPU, CUDA events; (b) the same K steps WITHOUT the collective -- the difference to ms_step
+    #      is the exposed part.  Last, because after (b) the ranks' weights differ.
+    allreduce_ms = allreduce_exposed_ms = 0.0
+    ms_local = ms_step
+    if world > 1:
+        flat = eng.store.G[:eng.store.count]
+        reduce_fn(flat)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.barrier()
+        a.record()
+        for _ in range(5):
+            reduce_fn(flat)
+        b.record()
+        ctx.barrier()
+        allreduce_ms = ctx.max_over_ranks(a.elapsed_time(b)) / 5
+        for _ in range(2):
+            step(x_dev, j_dev, v_dev, exchange=False)
+        ctx.barrier()
+        a.record()
+        for _ in range(steps):
+            step(x_dev, j_dev, v_dev, exchange=False)
+        b.record()
+        ctx.barrier()
+        ms_local = ctx.max_over_ranks(a.elapsed_time(b)) / steps
+        allreduce_exposed_ms = ms_step - ms_local
     # ---- roofline of the dominant kernel class
     hbm_peak, tf_burst, tf_sustained, peak_src = load_peaks()
     plan = eng.plans[(B, H, W)]
@@ -747,6 +766,7 @@ def bench_train(ctx: Ctx, args):
                          "# critical chain by class (launches, ms): " + "; ".join(f"{k} {v[0]} {v[1]:.3f}" for k, v in top_crit)],
                         classes, total_ms)
     launches = plan.num_kernel_launches
+    eng.release_graphs()                  # graphs holding NCCL nodes must go before the process group does (Ctx.close)
     flops_per_step = TRAIN_GFLOP_PER_IMAGE * 1e9 * B
     tf = flops_per_step / (ms_step * 1e-3) / 1e12
     nbytes_grad = eng.store.count * 4
@@ -757,6 +777,11 @@ def bench_train(ctx: Ctx, args):
         "config": train_config(world, B),
         "loss_first_last": [loss0, loss1],
         "allreduce_ms": allreduce_ms, "allreduce_bytes": nbytes_grad if world > 1 else 0,
+        "allreduce": {"overlapped_in_graph": bool(_tr.OVERLAP_ALLREDUCE) and world > 1,
+                      "buckets": len(eng.grad_buckets()) if world > 1 else 0,
+                      "alone_ms": allreduce_ms, "exposed_ms": allreduce_exposed_ms, "ms_per_step_without_exchange": ms_local,
+                      "note": "alone_ms: the whole flat fp32 gradient buffer all-reduced eagerly with nothing else on the "
+                              "GPU; exposed_ms: ms_per_step minus the same steps run without the collective"},
         "tensor_tflops": tf, "tensor_frac_of_measured_peak": tf / tf_sustained,
         "tensor_frac": {"of_sustained": tf / tf_sustained, "of_burst": tf / tf_burst, "of_nominal_2250": tf / 2250.0},
         "roofline": roofline, "launch_dag": dag_info,

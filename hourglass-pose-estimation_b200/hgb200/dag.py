@@ -283,7 +283,9 @@ def capture(fns: Sequence[Callable], stream_of: Sequence[int], waits: Sequence[S
             priorities: Optional[Sequence[int]] = None):
     """Capture `fns` into one CUDA graph across k streams.  Without `priorities` stream 0 is the capturing stream;
     with them every stream s is a fresh stream of priority priorities[s] (lower = more urgent, as CUDA counts) and the
-    capturing stream only forks and joins."""
+    capturing stream only forks and joins.  A closure may enqueue work through another library that is itself
+    capture-aware (the NCCL all-reduce nodes of the data-parallel step, hgb200/train.py): whatever it forks rejoins the
+    closure's stream before it returns."""
     g = torch.cuda.CUDAGraph()
     need_event = set()
     for w in waits:

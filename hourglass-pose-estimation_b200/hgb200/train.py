@@ -34,6 +34,12 @@ BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
 _ACT = torch.bfloat16     # activation / GEMM-weight storage type
+# Data parallel: the gradient all-reduce is issued PER BUCKET INSIDE the step's CUDA graph, on a stream of its own, as soon
+# as the last weight-gradient launch of the bucket has run (the hourglass of stack 8 first, ... , the stem last), so the
+# exchange over NVLink overlaps the rest of the backward pass.  Opt-in (HG_OVERLAP_AR=1); the default is one
+# all-reduce of the whole flat buffer after the graph.  A graph that holds NCCL nodes must be destroyed BEFORE the process
+# group is (ncclCommDestroy waits for it): call TrainEngine.release_graphs() first.
+OVERLAP_ALLREDUCE = os.environ.get("HG_OVERLAP_AR", "0") == "1"
 # The step's launches are captured as a dependency DAG across this many CUDA streams (hgb200/dag.py);
 # 1 = one chain on one stream.
 STREAMS = int(os.environ.get("HG_TRAIN_STREAMS", "16"))
@@ -388,6 +394,7 @@ class TrainPlan:
         self.grad_scale = 1.0          # 1/world_size: the sum over ranks is the global-batch mean
         self.use_target_weight = True
         self.graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        self._dp_fn = None
         self.fwd_bytes = 0
         self.bwd_arena_bytes = 0
         self.pending_backward = False       # autograd drop-in: a forward whose backward has not run yet
@@ -463,6 +470,38 @@ class TrainPlan:
             sched = self.schedules[(which, k)] = (d, stream_of, waits)
         return sched
 
+    def run_dp(self, all_reduce: Callable, buckets):
+        """The step with the per-bucket gradient all-reduce inside the same CUDA graph (see OVERLAP_ALLREDUCE)."""
+        g = self.graphs.get("step_dp")
+        if g is None or self._dp_fn != all_reduce:           # (bound methods compare equal by object and function)
+            g = self._capture_dp(all_reduce, buckets, "step_dp")
+            self._dp_fn = all_reduce
+        g.replay()
+
+    def comm_schedule(self, buckets):
+        """-> (stream index, waits) of the all-reduce nodes appended to launches("step"): every node goes to ONE extra
+        stream (index STREAMS) in bucket order and waits for the launches that last wrote its slice of the gradient buffer
+        (RAW edges of the launch DAG, built from the same byte-range records as everything else)."""
+        G = self.eng.store.G
+        lo_, hi_ = self._slice("step")
+        n_step = hi_ - lo_
+        comm_records = [[([], [dag._region(G[lo:hi])])] for lo, hi in buckets]
+        d = dag.build(self.records[lo_:hi_] + comm_records)
+        return STREAMS, [sorted(p for p in d.preds[n_step + j] if p < n_step) for j in range(len(buckets))]
+
+    def _capture_dp(self, all_reduce: Callable, buckets, key):
+        fns = self.launches("step")
+        G = self.eng.store.G
+        _, stream_of, waits = self.schedule("step")
+        comm_stream, comm_waits = self.comm_schedule(buckets)
+        comm_fns = [(lambda lo=lo, hi=hi: all_reduce(G[lo:hi])) for lo, hi in buckets]
+        prio = [-1] * (STREAMS - LEAF_STREAMS) + [0] * LEAF_STREAMS if (LEAF_STREAMS > 0 and STREAMS - LEAF_STREAMS >= 1) \
+            else [0] * STREAMS
+        g = dag.capture(fns + comm_fns, list(stream_of) + [comm_stream] * len(buckets), list(waits) + comm_waits,
+                        STREAMS + 1, self.eng.device, priorities=prio + [-1])
+        self.graphs[key] = g
+        return g
+
     def _capture(self, which: str):
         # The caller must have run the list eagerly once before (module loading, shared-memory opt-in, access
         # records) -- TrainEngine.plan_for() does that on a scratch copy of the BN statistics.
@@ -526,6 +565,8 @@ class TrainEngine:
         self.pack_table = ops.make_pack_table(self.pack_entries, device)
         self.plans: Dict[tuple, TrainPlan] = {}
         self.steps = 0
+        self._buckets = None
+        self._comm_warm = False
 
     # ------------------------------------------------------------------ construction helpers
     def alloc_bn_slot(self, c: int) -> int:
@@ -731,8 +772,6 @@ class TrainEngine:
         plan.pre.append(lambda: ops.pack_weights(self.pack_table, len(self.pack_entries), reads=reads, writes=w_dg, which=2))
 
         self._emit_backward(plan)
-        for rm in self.remap:
-            plan.post.append(lambda rm=rm: rm.chain(self.ones))
         return plan
 
     # ------------------------------------------------------------------ backward emission (reverse node order)
@@ -870,6 +909,12 @@ class TrainEngine:
                 B.append(lambda i=i, dhp=dhp: ops.nchw_to_nhwc_bf16_pad(plan.dheat[i], dhp))
                 B.append(lambda dhp=dhp, sc=sc, J=J, s=scr(dhp): ops.colstats(dhp, sc.gb, c_valid=J, scratch=s))
                 B.append(lambda dhp=dhp, sc=sc, xd=x.data, J=J: ops.wgrad(dhp, xd, sc.gw, co_valid=J, max_ctas=wg_ctas))
+                # the merged remap conv that follows this head has already left dWm / dbm (its backward runs first): spread
+                # them to score_ / score HERE, not at the end of the step, so that this stack's slice of the gradient
+                # buffer is final -- and can be exchanged -- as soon as its backward is
+                for rm in self.remap:
+                    if rm.score is sc:
+                        B.append(lambda rm=rm: rm.chain(self.ones))
                 if x.grad is None:
                     x.grad = arena.get(x.data.shape)
                     dgrad1x1(dhp, sc.wd, ch, x.grad)
@@ -953,12 +998,76 @@ class TrainEngine:
         self.steps += 1
         self.model._weights_epoch = getattr(self.model, "_weights_epoch", 0) + 1
 
+    def release_graphs(self):
+        """Drop every captured CUDA graph (they are re-captured on demand).  Required before
+        torch.distributed.destroy_process_group() when the step's graph holds the all-reduce nodes."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        for p in self.plans.values():
+            p.graphs.clear()
+            p._dp_fn = None
+
+    def grad_buckets(self):
+        """Slices [lo, hi) of the flat gradient buffer in the order the backward pass completes them: the hourglass of the
+        last stack first (13 of a stack's 14 bottlenecks live in `hg.<i>`, contiguous in named_parameters() order), then
+        down to stack 1, then everything else (stem, layer1-3, res / fc / score / remap convs: ~12 % of the parameters).
+        Identical on every rank (it depends on the parameter names only), so the ranks issue the same collectives in
+        the same order whether they run the graph, the eager list or idle_step()."""
+        if self._buckets is None:
+            st = self.store
+            spans = {}
+            for name, (off, n, _) in st.slots.items():
+                parts = name.split(".")
+                if parts[0] == "hg" and len(parts) > 2 and parts[1].isdigit():
+                    lo, hi = spans.get(int(parts[1]), (off, off))
+                    spans[int(parts[1])] = (min(lo, off), max(hi, off + _pad(n, 4)))
+            out, covered = [], []
+            for i in sorted(spans, reverse=True):
+                out.append(spans[i])
+                covered.append(spans[i])
+            covered.sort()
+            # the hourglass spans must be disjoint runs; whatever lies between / around them forms the closing buckets
+            pos, rest = 0, []
+            for lo, hi in covered:
+                if lo < pos:
+                    out, rest, pos = [], [], 0           # unexpected layout: one bucket
+                    break
+                if lo > pos:
+                    rest.append((pos, lo))
+                pos = hi
+            if pos < st.count:
+                rest.append((pos, st.count))
+            # order of completion in the backward pass: hg.<S-1> ... hg.<1>, then the block BEHIND the hourglasses (res / fc /
+            # score / remap convs of every stack: stack 1's are written before ITS hourglass is entered), then hg.<0>, and
+            # last the block in FRONT of them (stem, layer1-3) -- the only bucket whose exchange nothing can hide
+            if out and len(rest) == 2 and rest[0][0] == 0:
+                self._buckets = out[:-1] + [rest[1], out[-1], rest[0]]
+            else:
+                self._buckets = out + rest
+        return self._buckets
+
+    def _reduce_eager(self, all_reduce: Callable):
+        G = self.store.G
+        if OVERLAP_ALLREDUCE:
+            for lo, hi in self.grad_buckets():
+                all_reduce(G[lo:hi])
+        else:
+            all_reduce(G[:self.store.count])
+
+    def _comm_warmup(self, all_reduce: Callable):
+        """The communicator is created by the first collective: that must not happen under stream capture.  Every rank
+        passes here exactly once (its first train_step or idle_step), so the extra collective is symmetric."""
+        if OVERLAP_ALLREDUCE and not self._comm_warm:
+            self._comm_warm = True
+            all_reduce(torch.zeros(4, dtype=torch.float32, device=self.device))
+
     def idle_step(self, lr: float, all_reduce: Optional[Callable] = None):
-        """A rank whose shard of a (ragged, last) batch is empty still takes part in the step's collective: zero
+        """A rank whose shard of a (ragged, last) batch is empty still takes part in the step's collectives: zero
         gradients in, the other ranks' sum out, the same RMSprop update as everywhere else."""
         ops.zero_(self.store.G)
         if all_reduce is not None:
-            all_reduce(self.store.G[:self.store.count])
+            self._comm_warmup(all_reduce)
+            self._reduce_eager(all_reduce)
         self.rmsprop(lr)
 
     def train_step(self, x: torch.Tensor, target: torch.Tensor, target_weight: Optional[torch.Tensor], lr: float, *,
@@ -978,9 +1087,14 @@ class TrainEngine:
         if plan.grad_scale != gs or plan.use_target_weight != (target_weight is not None):
             plan.grad_scale, plan.use_target_weight = gs, target_weight is not None
             plan.graphs.clear()
-        plan.run("step", use_graph)
         if all_reduce is not None:
-            all_reduce(self.store.G[:self.store.count])
+            self._comm_warmup(all_reduce)
+        if all_reduce is not None and OVERLAP_ALLREDUCE and use_graph and STREAMS > 1:
+            plan.run_dp(all_reduce, self.grad_buckets())
+        else:
+            plan.run("step", use_graph)
+            if all_reduce is not None:
+                self._reduce_eager(all_reduce)
         self.rmsprop(lr)
         return plan.loss
 

@@ -151,3 +151,61 @@ def test_random_topological_orders_give_identical_steps(cpu_train, S, J, B, H, W
     for which in ("fwd", "bwd"):
         dd, so, _ = plan.schedule(which)
         assert dd.n == len(plan.launches(which))
+
+
+def test_gradient_buckets_and_their_place_in_the_launch_dag(monkeypatch):
+    """Data-parallel step (hgb200/train.py, OVERLAP_ALLREDUCE): the flat gradient buffer is cut into buckets that the
+    backward pass completes one after the other (hourglass of the last stack first), and every all-reduce node of the
+    step's graph waits for exactly the launches that last wrote its slice: each launch that writes into the bucket must be
+    an ancestor (or one) of the node's waits, and no wait may be a launch that does not touch the bucket's history."""
+    import hgb200.train as tr
+    from src.models import hg
+    monkeypatch.setattr(tr, "ops", fake_ops)
+    S, J, B, H, W = 3, 16, 2, 64, 64
+    model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum")
+    model.load_state_dict(make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, seed=0))
+    model.train()
+    eng = tr.TrainEngine(model, "cpu")
+    buckets = eng.grad_buckets()
+    st = eng.store
+    # a partition of [0, count): disjoint, complete; the first S buckets are hg.<S-1> ... hg.<0>
+    cover = sorted(buckets)
+    assert cover[0][0] == 0 and cover[-1][1] == st.count
+    assert all(a[1] == b[0] for a, b in zip(cover, cover[1:]))
+    # order: hg.<S-1> ... hg.<1>, the block behind the hourglasses, hg.<0>, the block in front of them (stem, layer1-3)
+    where = {i: (j if i > 0 else S) for j, i in enumerate(range(S - 1, -1, -1))}
+    for i, j in where.items():
+        names = [n for n in st.slots if n.startswith(f"hg.{i}.")]
+        lo = min(st.slots[n][0] for n in names)
+        hi = max(st.slots[n][0] + st.slots[n][1] for n in names)
+        assert buckets[j][0] == lo and hi <= buckets[j][1] <= hi + 3, (j, buckets[j], lo, hi)
+    assert len(buckets) == S + 2 and buckets[-1][0] == 0 and buckets[S - 1][1] == st.count
+    assert buckets[-1][1] - buckets[-1][0] < 0.06 * st.count                # what no launch can hide: stem + layer1-3
+    plan = eng.plan_for(B, H, W)
+    stream, waits = plan.comm_schedule(buckets)
+    assert stream == tr.STREAMS and len(waits) == len(buckets)
+    d, _, _ = plan.schedule("step")
+    gptr = st.G.untyped_storage().data_ptr()
+    anc_cache = {}
+
+    def ancestors(i):
+        if i not in anc_cache:
+            s = {i}
+            for p in d.preds[i]:
+                s |= ancestors(p)
+            anc_cache[i] = s
+        return anc_cache[i]
+
+    first_wait = []
+    for (lo, hi), w in zip(buckets, waits):
+        assert w, "every bucket has a writer"
+        closure = set()
+        for p in w:
+            closure |= ancestors(p)
+        writers = [i for i, rec in enumerate(plan.records)
+                   if any(acc != dag.BARRIER and any(r[0] == gptr and r[1] < hi * 4 and r[2] > lo * 4 for r in acc[1]) for acc in rec)]
+        assert writers and set(writers) <= closure
+        assert set(w) <= set(writers)                  # a node waits only for launches that write its own slice
+        first_wait.append(max(w))
+    # the buckets complete in the order they are issued on the exchange stream
+    assert first_wait == sorted(first_wait), first_wait
