@@ -101,8 +101,9 @@ def main():
     if "c4" in what:
         res.append(c4_train(ctx))
     if "c5" in what:
-        res.append(c5_sweep(ctx, 21))
-        res.append(c5_sweep(ctx, 14))
+        b = tuple(int(v) for v in os.environ.get("C5_BATCHES", "1,2,4,8,16,32,64,128").split(","))
+        res.append(c5_sweep(ctx, 21, batches=b))
+        res.append(c5_sweep(ctx, 14, batches=b))
     if ctx.rank == 0:
         for r in res:
             print(json.dumps(r), flush=True)
