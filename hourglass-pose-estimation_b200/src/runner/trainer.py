@@ -110,8 +110,10 @@ class Trainer(object):
             raise RuntimeError("Trainer (B200 build) needs a CUDA device: there is no CPU fallback")
         self.device = torch.device('cuda', local_rank)
         torch.cuda.set_device(self.device)
+        self._own_pg = False
         if self.world > 1 and not dist.is_initialized():
             dist.init_process_group(backend='nccl', device_id=self.device)
+            self._own_pg = True
         if self.rank == 0:
             print(f"==> creating model '{cfg['MODEL']['arch']}', stacks={cfg['MODEL']['num_stacks']}")
         torch.manual_seed(cfg.get('COMMON', {}).get('seed', 0))      # identical initial weights on every rank
@@ -246,6 +248,14 @@ class Trainer(object):
             self.best_acc = average_acc.avg
         return average_loss.avg, average_acc.avg, is_best
 
+    def close(self):
+        """Release the captured CUDA graphs and, if this Trainer created it, the process group -- in that order: a graph
+        that holds the all-reduce nodes (HG_OVERLAP_AR=1) must be destroyed before the NCCL communicator is."""
+        self.engine.release_graphs()
+        if self._own_pg and dist.is_initialized():
+            dist.destroy_process_group()
+            self._own_pg = False
+
     def train(self):
         only_checkpoint_path = os.path.join(self.cfg['COMMON']['checkpoint_dir'], 'ckpts')
         if self.rank == 0 and not os.path.isdir(only_checkpoint_path):
@@ -264,3 +274,4 @@ class Trainer(object):
                     torch.save(state, os.path.join(only_checkpoint_path, f'checkpoint_{epoch+1}.pth.tar'))
                 if is_best:
                     torch.save(state, os.path.join(only_checkpoint_path, 'best.pth.tar'))
+        self.engine.release_graphs()      # re-captured on demand; nothing that holds NCCL nodes outlives the process group
