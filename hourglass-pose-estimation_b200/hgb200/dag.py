@@ -96,6 +96,34 @@ def accesses(name: str, args: Sequence, kwargs: dict):
     return reads, writes
 
 
+class _RecordingGuard:
+    """The recording pass of a plan rebinds the module-global `ops` of hgb200.engine / hgb200.train to a recorder for its
+    duration.  That window is process-wide state: one recording at a time (a lock for other threads), and a nested plan
+    build from inside the window -- which would record, or launch, through the wrong object -- is refused."""
+
+    def __init__(self):
+        import threading
+        self._lock = threading.Lock()
+        self._owner = None
+
+    def __enter__(self):
+        import threading
+        me = threading.get_ident()
+        if self._owner == me:
+            raise RuntimeError("a launch plan is being recorded on this thread: plans cannot be built from inside that pass")
+        self._lock.acquire()
+        self._owner = me
+        return self
+
+    def __exit__(self, *exc):
+        self._owner = None
+        self._lock.release()
+        return False
+
+
+RECORDING = _RecordingGuard()
+
+
 class Recorder:
     """Wraps a module of launch wrappers (hgb200.ops) for one eager pass: records, per call, what it reads and
     writes.  `calls` is reset by the caller before each closure."""

@@ -142,19 +142,20 @@ class Plan:
         # warm up on a side stream (lazy module loading, smem attribute opt-in) while recording what every launch
         # reads and writes, then capture -- as a launch DAG over several streams when STREAMS > 1
         global ops
-        rec = dag.Recorder(ops)
-        real_ops, ops = ops, rec
         self.records = []
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
-        try:
-            with torch.cuda.stream(s):
-                for fn in self.launches:
-                    rec.calls = []
-                    fn()
-                    self.records.append(rec.calls)
-        finally:
-            ops = real_ops
+        with dag.RECORDING:                 # the rebinding of `ops` below is process-wide: one recording at a time
+            rec = dag.Recorder(ops)
+            real_ops, ops = ops, rec
+            try:
+                with torch.cuda.stream(s):
+                    for fn in self.launches:
+                        rec.calls = []
+                        fn()
+                        self.records.append(rec.calls)
+            finally:
+                ops = real_ops
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         ops.check_err_word(self.device)

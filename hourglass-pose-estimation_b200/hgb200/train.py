@@ -956,6 +956,8 @@ class TrainEngine:
             bufs = [(b.rm, b.rv, b.nbt) for b in self._bns]
             keep = [(a.clone(), b.clone(), c.clone()) for a, b, c in bufs]
             global ops
+            guard = dag.RECORDING           # the rebinding of `ops` below is process-wide: one recording at a time
+            guard.__enter__()
             rec = _Recorder(ops)
             real_ops, ops = ops, rec
 
@@ -980,6 +982,7 @@ class TrainEngine:
                     record()
             finally:
                 ops = real_ops
+                guard.__exit__(None, None, None)
             if cuda:
                 ops.check_err_word(self.device)
             for (a, b, c), (ka, kb, kc) in zip(bufs, keep):

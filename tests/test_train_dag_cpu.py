@@ -209,3 +209,14 @@ def test_gradient_buckets_and_their_place_in_the_launch_dag(monkeypatch):
         first_wait.append(max(w))
     # the buckets complete in the order they are issued on the exchange stream
     assert first_wait == sorted(first_wait), first_wait
+
+
+def test_recording_window_is_exclusive():
+    """The recording pass rebinds hgb200.train.ops / hgb200.engine.ops process-wide (dag.RECORDING): a nested plan build on
+    the same thread is refused instead of recording through the wrong object, and the guard is free again afterwards."""
+    with dag.RECORDING:
+        with pytest.raises(RuntimeError):
+            with dag.RECORDING:
+                pass
+    with dag.RECORDING:
+        pass
