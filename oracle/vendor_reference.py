@@ -2,8 +2,9 @@
 not exist (the GPU box).  Test / baseline infrastructure only (see oracle/__init__.py).
 
 The reference is pure Python with no build or install metadata (no setup.py / pyproject), so "building" it is a byte copy
-of the files the path needs -- `src/__init__.py`, `src/models/*`, `src/loss/*`, `src/utils/*`, and the entry script
-`scripts/estimate.py` whose flow tests/test_gpu_dropin.py executes against this repo's `src` -- from where they lie under
+of the files the path needs -- `src/__init__.py`, `src/models/*`, `src/loss/*`, `src/utils/*`, `src/datasets/*` (the dataset
+classes this repo's `src.datasets` re-exports), and the entry scripts `scripts/estimate.py` and `scripts/train_and_evaluate.py`
+whose flows tests/test_gpu_dropin.py executes against this repo's `src` -- from where they lie under
 /root/reference into `oracle/_ref/`, plus a MANIFEST.json with each file's sha256.  `oracle/_ref/` is git-ignored (no
 reference source enters the history) but travels with `gpurun`.  `__graft_entry__.build()` runs this when /root/reference
 is present; `bench.py --impl reference` and the `gpu_baseline` leg import the copy (`kind: "reference"`) and fall back to
@@ -21,8 +22,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEST = os.path.join(HERE, "_ref")
-PARTS = ("__init__.py", "models", "loss", "utils")
-SCRIPTS = ("scripts/estimate.py",)
+PARTS = ("__init__.py", "models", "loss", "utils", "datasets")
+SCRIPTS = ("scripts/estimate.py", "scripts/train_and_evaluate.py")
 
 
 def vendor(reference_root: str = "/root/reference") -> bool:

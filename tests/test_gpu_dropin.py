@@ -200,3 +200,78 @@ def test_reference_estimate_script_runs_unmodified_over_this_src(tmp_path, monke
     assert "creating model 'hg', stacks=2" in out and "Inference time on cuda" in out
     drawn = cv2.imread(str(dest))
     assert drawn is not None and drawn.shape == frame.shape and (drawn != frame).any()      # the key points were drawn
+
+
+def _write_mpii_fixture(root, n_train=8, n_val=4, seed=0):
+    """A tiny dataset in the MPII layout the reference's `mpii` class reads (datasets/mpii.py:42-88): images/*.png,
+    annot/{train,valid}.json with 1-based joints, person centre and scale (height / 200)."""
+    import json
+    import cv2
+    rng = np.random.RandomState(seed)
+    os.makedirs(os.path.join(root, "images"))
+    os.makedirs(os.path.join(root, "annot"))
+    for split, n in (("train", n_train), ("valid", n_val)):
+        anno = []
+        for i in range(n):
+            img = (rng.rand(300, 300, 3) * 40).astype(np.uint8)
+            joints = rng.uniform(60, 240, (16, 2))
+            for j, (x, y) in enumerate(joints):
+                cv2.circle(img, (int(x), int(y)), 6, (int(37 * j) % 256, int(91 * j) % 256, 255 - 13 * j), -1)
+            name = f"{split}_{i:03d}.png"
+            cv2.imwrite(os.path.join(root, "images", name), img)
+            anno.append({"image": name, "center": [150.0, 150.0], "scale": 1.2, "joints": (joints + 1).tolist(),
+                         "joints_vis": [1] * 16})
+        with open(os.path.join(root, "annot", f"{split}.json"), "w") as f:
+            json.dump(anno, f)
+
+
+def test_reference_train_script_runs_unmodified_over_this_src(tmp_path, monkeypatch, capsys):
+    """scripts/train_and_evaluate.py of the reference, byte for byte (vendored into oracle/_ref), with THIS repo's `src` on
+    the path: yaml -> `from src import datasets, models` (the reference's own `mpii` dataset class, re-exported by
+    src.datasets, reading an MPII-layout fixture through this build's src.utils.transforms) -> Trainer(cfg, n_joints)
+    building its DataLoaders -> trainer.train(): two epochs of the sm_100a training step, evaluation, checkpoints in the
+    reference's format.  Environment shims only: numpy >= 1.24 dropped `np.float` (mpii.py:53), `torchsummary` (imported
+    by the script, used by its evaluate-only branch) is not installed."""
+    import runpy
+    import sys
+    import types
+    import yaml
+    from oracle.vendor_reference import verify, DEST
+    script = os.path.join(DEST, "scripts", "train_and_evaluate.py")
+    if not (verify() and os.path.isfile(script) and os.path.isfile(os.path.join(DEST, "src", "datasets", "mpii.py"))):
+        pytest.skip("oracle/_ref is not vendored in this checkout (python oracle/vendor_reference.py)")
+    data = tmp_path / "mpii"
+    _write_mpii_fixture(str(data))
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data/mpii")                       # mpii.py:27: './data/mpii/mean.pth.tar', relative to the working directory
+    torch.save({"mean": torch.tensor([0.45, 0.45, 0.45]), "std": torch.tensor([0.25, 0.25, 0.25])}, "data/mpii/mean.pth.tar")
+    monkeypatch.setattr(np, "float", float, raising=False)
+    monkeypatch.setitem(sys.modules, "torchsummary", types.SimpleNamespace(summary=lambda *a, **k: None))
+    monkeypatch.setenv("HG_REFERENCE_SRC", os.path.join(DEST, "src"))
+    for name in [m for m in sys.modules if m == "src.datasets" or m.startswith("src.datasets.")]:
+        monkeypatch.delitem(sys.modules, name)      # re-import src.datasets with the vendored checkout in view
+    import src
+    if hasattr(src, "datasets"):
+        monkeypatch.delattr(src, "datasets")
+    ckdir = tmp_path / "ck"
+    cfg = {"DATASET": {"name": "mpii", "image_path": str(data / "images"), "annotation_path": str(data / "annot"),
+                       "inp_res": 256, "out_res": 64, "flip": True, "sigma": 1, "scale_factor": 0.25, "rot_factor": 30,
+                       "label_type": "Gaussian"},
+           "MODEL": {"arch": "hg", "num_stacks": 2, "mobile": False, "skip_mode": "sum", "subset": None},
+           "COMMON": {"checkpoint_dir": str(ckdir), "snapshot": 1, "resume": "", "evaluate_only": False, "pck": 0.5,
+                      "gpu": os.environ.get("CUDA_VISIBLE_DEVICES", "0")},
+           "TRAIN": {"num_workers": 0, "epochs": 1, "start_epoch": 0, "train_batch": 4, "val_batch": 4,
+                     "learning_rate": 2.5e-4, "schedule": [1], "gamma": 0.1}}
+    cfg_path = tmp_path / "train.yaml"
+    cfg_path.write_text(yaml.safe_dump(cfg))
+    monkeypatch.setattr(sys, "argv", [script, str(cfg_path)])
+    runpy.run_path(script, run_name="__main__")
+    out = capsys.readouterr().out
+    assert "creating model 'hg', stacks=2" in out and "Epoch: 2" in out
+    from src import datasets
+    assert datasets.REFERENCE_DATASETS == os.path.join(DEST, "src", "datasets") and datasets.mpii.__module__ == "src.datasets.mpii"
+    ck = ckdir / "mpii_hg_s2_non-mobile_all" / "ckpts" / "checkpoint_2.pth.tar"
+    assert ck.is_file()
+    state = torch.load(str(ck), map_location="cpu", weights_only=False)
+    assert state["epoch"] == 2 and all(k.startswith("module.") for k in state["state_dict"])
+    assert all(torch.isfinite(v).all() for v in state["state_dict"].values() if v.is_floating_point())
