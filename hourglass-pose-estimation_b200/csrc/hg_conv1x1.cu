@@ -64,6 +64,9 @@ struct Params {
     // consecutive pixels, so that the geometric epilogues (halo / 4-D store, upsample operand) work for any width <= 128;
     // the rest of the 128-row MMA tile computes on stale shared memory and is clipped by the 4-D TMA store.
     int tile_pixels, tiles_per_img, img_hw;
+    // kPoolIn: the prologue warps also write the 2x2 max-pool of the RAW input tile (hg_conv_desc.pool_in)
+    __nv_bfloat16* pool_in;
+    int pool_in_w, pool_in_shift;   // image width; log2 of the pooled width
 };
 
 __device__ __forceinline__ int tile_m0(const Params& p, int tile) {
@@ -88,7 +91,8 @@ __device__ __forceinline__ uint32_t bf16x2_max_u32(uint32_t a, uint32_t b) {
 // kRagged: halo-padded output for image sizes whose 128-pixel tiles are not whole image rows (e.g. the 64x48 heat-map
 // grid of 256x192 inputs): the 4-D strided TMA store needs a rectangular box, so each epilogue thread stores its own
 // pixel's channels at the pixel's halo position instead (like the 3x3 kernel's epilogue); pads are never written.
-template <int BLOCK_N, bool kPrologue, bool kStats, bool kPool, bool kRagged = false>
+// kPoolIn: see Params::pool_in (prologue kernels only).
+template <int BLOCK_N, bool kPrologue, bool kStats, bool kPool, bool kRagged = false, bool kPoolIn = false>
 __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const __grid_constant__ Params p) {
     constexpr int kBStage = BLOCK_N * kBlockK * 2;
     constexpr int kSlabs = BLOCK_N / 64;
@@ -472,9 +476,30 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                     uint4 d[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {                        // all eight loads in flight before any use
-                        const int row = i * 16 + w * 4 + rsub;           // a quarter-warp owns one 128-byte row
+                        int row = i * 16 + w * 4 + rsub;                 // a quarter-warp owns one 128-byte row
+                        if (kPoolIn) {
+                            // the eight rows of a thread are two whole 2x2 pooling windows: pooled pixel q of the tile's 32,
+                            // window element e = (dy, dx)
+                            const int q = (w * 4 + rsub) * 2 + (i >> 2), e = i & 3;
+                            const int qy = q >> p.pool_in_shift, qx = q - (qy << p.pool_in_shift);
+                            row = (2 * qy + (e >> 1)) * p.pool_in_w + 2 * qx + (e & 1);
+                        }
                         addr[i] = a_base + row * 128 + ((c ^ (row & 7)) << 4);
                         d[i] = lds128(addr[i]);
+                    }
+                    if (kPoolIn) {
+                        // max over each window of the RAW values (what F.max_pool2d sees), 8 channels per thread: a
+                        // quarter-warp writes 128 contiguous bytes of the pooled pixel's row
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            uint4 m;
+                            m.x = bf16x2_max_u32(bf16x2_max_u32(d[h2 * 4].x, d[h2 * 4 + 1].x), bf16x2_max_u32(d[h2 * 4 + 2].x, d[h2 * 4 + 3].x));
+                            m.y = bf16x2_max_u32(bf16x2_max_u32(d[h2 * 4].y, d[h2 * 4 + 1].y), bf16x2_max_u32(d[h2 * 4 + 2].y, d[h2 * 4 + 3].y));
+                            m.z = bf16x2_max_u32(bf16x2_max_u32(d[h2 * 4].z, d[h2 * 4 + 1].z), bf16x2_max_u32(d[h2 * 4 + 2].z, d[h2 * 4 + 3].z));
+                            m.w = bf16x2_max_u32(bf16x2_max_u32(d[h2 * 4].w, d[h2 * 4 + 1].w), bf16x2_max_u32(d[h2 * 4 + 2].w, d[h2 * 4 + 3].w));
+                            const long long q = static_cast<long long>(tile) * 32 + (w * 4 + rsub) * 2 + h2;
+                            stg_v4(p.pool_in + q * p.cin + kb * kBlockK + c * 8, m);
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -541,9 +566,9 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t r
     return HG_OK;
 }
 
-template <int BLOCK_N, bool kPrologue, bool kStats, bool kPool = false, bool kRagged = false>
+template <int BLOCK_N, bool kPrologue, bool kStats, bool kPool = false, bool kRagged = false, bool kPoolIn = false>
 static int launch_variant(const Params& kp, int smem_bytes, cudaStream_t stream) {
-    auto kern = conv1x1_kernel<BLOCK_N, kPrologue, kStats, kPool, kRagged>;
+    auto kern = conv1x1_kernel<BLOCK_N, kPrologue, kStats, kPool, kRagged, kPoolIn>;
     static std::mutex mu;
     static unsigned long long done_mask = 0;
     int dev = 0;
@@ -614,6 +639,14 @@ int conv1x1_supported(const hg_conv_desc* d) {
     if (k > c1::kMaxK || static_cast<long long>(k) * d->cout * 2 > 128 * 1024) return 0;
     if (d->in_scale != nullptr && d->cout == 256) return 0;
     if (geometry_mode(d) == kGeomNone) return 0;
+    if (d->pool_in != nullptr) {
+        // the pooled INPUT as a second output of the prologue warps: flat 128-pixel tiles made of whole 2x2 windows
+        const int w = d->w, h = d->h;
+        const bool pow2 = (w & (w - 1)) == 0;
+        if (d->in_scale == nullptr || d->cout != 128 || d->cin2 != 0 || d->stats != nullptr || d->pool_out != nullptr) return 0;
+        if (geometry_mode(d) != kGeomFlat) return 0;
+        if (!pow2 || w > 64 || w < 2 || (h & 1) || 128 % (2 * w) != 0 || (static_cast<long long>(d->n) * h * w) % 128 != 0) return 0;
+    }
     if (d->pool_out != nullptr) {
         // the fused max-pool output: 256-channel results without prologue / statistics, whole 2x2 windows per tile
         const int w = d->w, h = d->h;
@@ -725,6 +758,15 @@ int conv1x1_launch(const hg_conv_desc* d, cudaStream_t stream) {
     if (d->pool_out) {
         if ((rc = make_map(&kp.map_pool, d->pool_out, d->cout, m / 4, kUpRows)) != HG_OK) return rc;
         return launch_variant<256, false, false, true>(kp, smem_bytes, stream);
+    }
+
+    if (d->pool_in) {
+        kp.pool_in = static_cast<__nv_bfloat16*>(d->pool_in);
+        kp.pool_in_w = d->w;
+        int sh = 0;
+        while ((2 << sh) < d->w) ++sh;                     // log2(w / 2)
+        kp.pool_in_shift = sh;
+        return launch_variant<128, true, false, false, false, true>(kp, smem_bytes, stream);
     }
 
     if (ragged) {

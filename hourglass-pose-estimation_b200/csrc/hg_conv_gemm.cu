@@ -549,6 +549,11 @@ extern "C" int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream_v) {
         if (!force_generic && conv1x1_supported(d)) return conv1x1_launch(d, stream);
     }
 
+    if (d->pool_in) {
+        set_last_error("hg_conv_nhwc_bf16: pool_in needs a 1x1 conv with prologue, cout 128, cin2 0, no stats, w a power of two "
+                       "<= 64 with 128 %% (2*w) == 0 and even h");
+        return HG_ERR_INVALID;
+    }
     if (d->pool_out) {
         set_last_error("hg_conv_nhwc_bf16: pool_out needs a 1x1 conv with cout 256, no prologue / stats / out_halo, w a power of two "
                        "<= 64 with 128 %% (2*w) == 0 and even h");

@@ -25,7 +25,7 @@ class ConvDesc(C.Structure):
         ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
         ("cin", C.c_int32), ("cin2", C.c_int32), ("cout", C.c_int32),
         ("ksize", C.c_int32), ("relu", C.c_int32), ("out_halo", C.c_int32),
-        ("stats", C.c_void_p), ("pool_out", C.c_void_p),
+        ("stats", C.c_void_p), ("pool_out", C.c_void_p), ("pool_in", C.c_void_p),
     ]
 
 

@@ -27,7 +27,7 @@ import torch
 # read-modify-write (accumulations): they order like writes.
 _WRITES: Dict[str, Tuple[Tuple, Tuple]] = {
     # name: (written positional indices, written keyword names)
-    "conv_nhwc": ((), ("out", "out_nchw_f32", "out_halo", "stats", "pool_out")),
+    "conv_nhwc": ((), ("out", "out_nchw_f32", "out_halo", "stats", "pool_out", "pool_in")),
     "conv3x3_halo": ((), ("out", "stats")),
     "conv3x3_k3_fused": ((), ("out",)),
     "dwconv3x3": ((), ("out",)),

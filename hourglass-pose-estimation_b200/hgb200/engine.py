@@ -51,6 +51,10 @@ FUSE_POOL = os.environ.get("HG_NO_POOL_FUSION", "0") != "1"
 # for the CTA pairs: bit-identical to the two kernels, 10-17 % faster on the pair, +4-5 % on the C2 step.
 # HG_NO_FUSE_K3=1 keeps the two kernels.
 FUSE_K3 = os.environ.get("HG_NO_FUSE_K3") is None
+# The 2x2 max-pool of a hourglass level's input comes out of the PROLOGUE of the 1x1 conv that opens the level's `up1`
+# bottleneck (hg_conv_desc.pool_in): both read the same tensor (src/models/modules.py:81-83), so that conv is emitted first and
+# the pool kernel with its re-read of the 256-channel tensor disappears.  HG_NO_POOL_IN=1 keeps the pool kernel.
+POOL_IN = os.environ.get("HG_NO_POOL_IN") is None
 
 
 def _host_copy(t: torch.Tensor) -> torch.Tensor:
@@ -302,7 +306,26 @@ class HourglassEngine:
                                            pool_out=pool_targets.get(idx)))
             return out
 
-        def block(bw: BlockWeights, x, up_low=None):
+        def halo_path(bw: BlockWeights, x) -> bool:
+            bn_, bh_, bw_, _ = x.shape
+            return (not bw.depthwise and bw_ >= halo_min_w and bw_ <= 253 and bw.planes in (64, 128) and x.shape[3] <= 512
+                    and (ragged_halo or (bw_ <= 128 and 128 % bw_ == 0 and (bh_ * bw_) % 128 == 0)))
+
+        def block_head(bw: BlockWeights, x, pool_in=None):
+            """The bottleneck's opening 1x1 (bn1 + ReLU prologue) into the halo-padded layout; optionally the 2x2 max-pool
+            of x as the prologue's second output."""
+            bn_, bh_, bw_, _ = x.shape
+            a2h = arena.get_halo(bn_, bh_, bw_, bw.planes)
+            pixels = bn_ * bh_ * bw_
+            plan.meta.append(dict(op=f"conv1x1_k{x.shape[3]}_n{bw.planes}_{bh_}x{bw_}_pro_halo" + ("_poolin" if pool_in is not None else ""),
+                                  kind="conv", flops=2.0 * pixels * x.shape[3] * bw.planes,
+                                  bytes=pixels * (x.shape[3] + bw.planes) * 2 + bw.w1.numel() * 2
+                                  + (pool_in.numel() * 2 if pool_in is not None else 0)))
+            L.append(lambda: ops.conv_nhwc(x, bw.w1, bw.b1, ksize=1, cout=bw.planes, relu=True, in_scale=bw.s1,
+                                           in_shift=bw.t1, out_halo=a2h, pool_in=pool_in))
+            return a2h
+
+        def block(bw: BlockWeights, x, up_low=None, head=None):
             bn_, bh_, bw_, _ = x.shape
             if bw.depthwise:
                 # mobile=True: K2 is a depthwise 3x3 stencil on CUDA cores (9 MAC/element, HBM-bound)
@@ -312,16 +335,10 @@ class HourglassEngine:
                                       flops=2.0 * bn_ * bh_ * bw_ * 9 * bw.planes, bytes=a2.numel() * 4))
                 L.append(lambda: ops.dwconv3x3(a2, bw.w2, bw.b2, relu=True, out=a3))
                 arena.put(a2)
-            elif (bw_ >= halo_min_w and bw_ <= 253 and bw.planes in (64, 128) and x.shape[3] <= 512
-                    and (ragged_halo or (bw_ <= 128 and 128 % bw_ == 0 and (bh_ * bw_) % 128 == 0))):
+            elif halo_path(bw, x):
                 # K1 writes the halo-padded layout; K2 reads every input pixel once (hg_conv3x3.cu)
-                a2h = arena.get_halo(bn_, bh_, bw_, bw.planes)
+                a2h = head if head is not None else block_head(bw, x)
                 pixels = bn_ * bh_ * bw_
-                plan.meta.append(dict(op=f"conv1x1_k{x.shape[3]}_n{bw.planes}_{bh_}x{bw_}_pro_halo", kind="conv",
-                                      flops=2.0 * pixels * x.shape[3] * bw.planes,
-                                      bytes=pixels * (x.shape[3] + bw.planes) * 2 + bw.w1.numel() * 2))
-                L.append(lambda: ops.conv_nhwc(x, bw.w1, bw.b1, ksize=1, cout=bw.planes, relu=True, in_scale=bw.s1,
-                                               in_shift=bw.t1, out_halo=a2h))
                 if (FUSE_K3 and bw.planes == 128 and not bw.downsample and bw.cout == 256
                         and ops.conv3x3_k3_fusable(bn_, bh_, bw_)):
                     # K2 + K3 in one launch on CTA pairs: the 3x3's result never leaves the SM (hg_conv3x3_k3_fused_bf16)
@@ -352,11 +369,12 @@ class HourglassEngine:
             arena.put(a3)
             return out
 
-        def chain(blocks, x, up_low=None, keep_input=True):
-            """nn.Sequential of bottlenecks; `up_low` joins the LAST block's epilogue."""
+        def chain(blocks, x, up_low=None, keep_input=True, head=None):
+            """nn.Sequential of bottlenecks; `up_low` joins the LAST block's epilogue; `head`: the first block's opening
+            1x1 has already been emitted (block_head)."""
             cur = x
             for i, bw in enumerate(blocks):
-                nxt = block(bw, cur, up_low if i == len(blocks) - 1 else None)
+                nxt = block(bw, cur, up_low if i == len(blocks) - 1 else None, head if i == 0 else None)
                 if cur is not x or not keep_input:
                     arena.put(cur)
                 cur = nxt
@@ -379,7 +397,17 @@ class HourglassEngine:
 
         def hourglass(levels, d, x, cat=None):
             """Hourglass._hour_glass_forward(n=d+1, x); x stays owned by the caller."""
-            p = pool(x)
+            head = None
+            up_first = levels[d][0][0]
+            nb_, hh_, ww_, c_ = x.shape
+            if (POOL_IN and cat is None and x.data_ptr() not in producer and halo_path(up_first, x) and up_first.planes == 128
+                    and not up_first.downsample and ops.conv_pool_in_fusable(nb_, hh_, ww_, up_first.planes)):
+                # up1's opening 1x1 first: its prologue warps hold every tile of x in shared memory and write the pooled
+                # tensor on the way; its halo-padded result waits for the lower pyramid (up1's tail takes low3 along)
+                p = arena.get((nb_, hh_ // 2, ww_ // 2, c_))
+                head = block_head(up_first, x, pool_in=p)
+            else:
+                p = pool(x)
             low1 = chain(levels[d][1], p, keep_input=False)
             if d > 0:
                 low2 = hourglass(levels, d - 1, low1, cat)
@@ -388,7 +416,7 @@ class HourglassEngine:
                 low2 = chain(levels[0][3], low1, keep_input=False)
             low3 = chain(levels[d][2], low2, keep_input=False)
             if cat is None:
-                out = chain(levels[d][0], x, up_low=low3)
+                out = chain(levels[d][0], x, up_low=low3, head=head)
                 arena.put(low3)
                 return out
             # skip_mode='concat': grouped 1x1 over cat([up1, upsample(low3)]) as two zero-padded GEMMs (fold.py)

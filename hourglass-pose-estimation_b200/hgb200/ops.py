@@ -63,7 +63,7 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
               x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
               out_nchw_f32: Optional[torch.Tensor] = None, heads: bool = False,
               out_halo: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None,
-              pool_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              pool_out: Optional[torch.Tensor] = None, pool_in: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Implicit-GEMM conv on tcgen05 (hg_conv_nhwc_bf16).
 
     x: bf16 [n,h,w,cin]; weight: bf16 [cout_pad, taps*cin (+cin2)]; bias fp32 [cout_pad].
@@ -72,6 +72,8 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
     batch statistics of the train-mode BatchNorm that follows).
     pool_out: bf16 [n,h/2,w/2,cout], additionally receives max_pool2d(result, 2, 2) from the same epilogue
     (see conv_pool_fusable).
+    pool_in: bf16 [n,h/2,w/2,cin], additionally receives max_pool2d(x, 2, 2) of the RAW input from the prologue warps of a
+    1x1 conv with in_scale / in_shift (see conv_pool_in_fusable).
     """
     _require_cuda(x, weight, bias, in_scale, in_shift, residual, up_low, x2, out, out_nchw_f32, stats)
     _check_stats(stats, cout)
@@ -86,6 +88,13 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
             raise HgError("conv_nhwc: pool_out must be bf16 [n,h/2,w/2,cout]")
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16 or (bias is not None and bias.dtype != torch.float32):
         raise HgError("conv_nhwc: x/weight must be bf16 and bias fp32")
+    if pool_in is not None:
+        _require_cuda(pool_in)
+        if (not conv_pool_in_fusable(x.shape[0], x.shape[1], x.shape[2], cout) or ksize != 1 or heads or in_scale is None
+                or stats is not None or pool_out is not None or x2 is not None):
+            raise HgError("conv_nhwc: pool_in needs a 1x1 conv with prologue and cout 128 on a level conv_pool_in_fusable() accepts")
+        if tuple(pool_in.shape) != (x.shape[0], x.shape[1] // 2, x.shape[2] // 2, x.shape[3]) or pool_in.dtype != torch.bfloat16:
+            raise HgError("conv_nhwc: pool_in must be bf16 [n,h/2,w/2,cin]")
     n, h, w, cin = x.shape
     cin2 = 0 if x2 is None else x2.shape[-1]
     cout_pad = (cout + 15) // 16 * 16
@@ -124,6 +133,7 @@ def conv_nhwc(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, *, ksiz
     d.err_word = err_word(x.device).data_ptr()
     d.stats = stats.data_ptr() if stats is not None else None
     d.pool_out = pool_out.data_ptr() if pool_out is not None else None
+    d.pool_in = pool_in.data_ptr() if pool_in is not None else None
     d.n, d.h, d.w, d.cin, d.cin2, d.cout, d.ksize, d.relu = n, h, w, cin, cin2, cout, ksize, int(relu)
     lib.check(lib.hg_conv_nhwc_bf16(C.byref(d), _stream()), "hg_conv_nhwc_bf16")
     return result
@@ -134,6 +144,13 @@ def conv_pool_fusable(h: int, w: int, cout: int, k: int) -> bool:
     128-pixel tile must hold whole pooling windows, and K = cin (+cin2) <= 128 so that the pooled staging slabs fit
     beside the resident weights without shrinking the staging ring."""
     return cout == 256 and k <= 128 and 2 <= w <= 64 and (w & (w - 1)) == 0 and h % 2 == 0 and 128 % (2 * w) == 0
+
+
+def conv_pool_in_fusable(n: int, h: int, w: int, cout: int) -> bool:
+    """Whether a 1x1 conv with prologue can also write the 2x2 max-pool of its RAW input (pool_in): flat 128-pixel tiles made
+    of whole pooling windows, 128 output channels."""
+    return (cout == 128 and 2 <= w <= 64 and (w & (w - 1)) == 0 and h % 2 == 0 and 128 % (2 * w) == 0
+            and (n * h * w) % 128 == 0 and (h * w) % 128 == 0)
 
 
 def stem_im2col(x_nchw: torch.Tensor, flip_w: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -33,7 +33,7 @@ extern "C" {
 #define HG_ERR_ARCH (-3)     /* device is not sm_100 */
 #define HG_ERR_DEVICE (-4)   /* a kernel reported a protocol timeout through its error word */
 
-#define HG_API_VERSION 8
+#define HG_API_VERSION 9
 
 int hg_api_version(void);
 /* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
@@ -82,6 +82,12 @@ typedef struct hg_conv_desc {
                                 (the hourglass pools every level's input, src/models/modules.py:82), written by the
                                 same epilogue.  1x1 only: cout 256, cin + cin2 <= 128, no prologue / stats / out_halo,
                                 w a power of two <= 64 with 128 %% (2*w) == 0, even h                              */
+    void* pool_in;           /* optional second output: F.max_pool2d(in, 2, stride=2) of the RAW input (before the
+                                in_scale / in_shift prologue) as bf16 NHWC [n][h/2][w/2][cin].  Hourglass pools the very
+                                tensor its `up1` bottleneck opens with (src/models/modules.py:81-83): the 1x1 kernel's
+                                prologue warps already hold every input tile in shared memory, so the pool kernel's re-read
+                                of the tensor disappears.  1x1 with prologue only: cout 128, cin2 = 0, no stats, w a power
+                                of two <= 64 with 128 %% (2*w) == 0, even h (128-pixel tiles hold whole 2x2 windows)   */
 } hg_conv_desc;
 
 int hg_conv_nhwc_bf16(const hg_conv_desc* d, void* stream);

@@ -34,8 +34,10 @@ def _store(out, y_nchw):
 
 
 def conv_nhwc(x, weight, bias, *, ksize, cout, relu=False, in_scale=None, in_shift=None, residual=None, up_low=None,
-              x2=None, out=None, out_nchw_f32=None, heads=False, out_halo=None, stats=None, pool_out=None):
+              x2=None, out=None, out_nchw_f32=None, heads=False, out_halo=None, stats=None, pool_out=None, pool_in=None):
     n, h, w, cin = x.shape
+    if pool_in is not None:               # the 2x2 max-pool of the RAW input (before the prologue)
+        _store(pool_in, F.max_pool2d(_nchw(x), 2, 2))
     taps = ksize * ksize
     wm = weight.float()[:cout]
     w4 = wm[:, :taps * cin].reshape(cout, ksize, ksize, cin).permute(0, 3, 1, 2)

@@ -281,6 +281,37 @@ def test_stem_window_conv(shape, ops, dev):
         err = float((out.float().permute(0, 3, 1, 2) - ref).abs().max())
         assert err <= float(ref.abs().max()) * 2 ** -7, f"err {err}"
 
+@pytest.mark.parametrize("shape", [(2, 64, 64, 256), (3, 32, 32, 256), (8, 16, 16, 256), (2, 64, 64, 128), (5, 32, 32, 256), (1, 8, 8, 256)])
+def test_conv1x1_prologue_also_writes_the_pooled_input(shape, ops, dev):
+    """hg_conv_desc.pool_in: the 2x2 max-pool of the RAW input (what Hourglass pools, src/models/modules.py:82) as a second
+    output of the prologue warps -- bit-identical to the pool kernel, and the conv's own halo-padded result unchanged."""
+    from hgb200 import HgError
+    n, h, w, cin = shape
+    cout = 128
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(n, h, w, cin, generator=g).to(torch.bfloat16).to(dev)
+    wt = (torch.randn(cout, cin, generator=g) / cin ** 0.5).to(torch.bfloat16).to(dev)
+    bias = (torch.randn(cout, generator=g) * 0.5).to(dev)
+    scale = (0.5 + torch.rand(cin, generator=g)).to(dev)
+    shift = (0.3 * torch.randn(cin, generator=g)).to(dev)
+    assert ops.conv_pool_in_fusable(n, h, w, cout) == ((n * h * w) % 128 == 0)
+    if not ops.conv_pool_in_fusable(n, h, w, cout):
+        with pytest.raises(HgError):
+            ops.conv_nhwc(x, wt, bias, ksize=1, cout=cout, relu=True, in_scale=scale, in_shift=shift,
+                          pool_in=torch.empty(n, h // 2, w // 2, cin, dtype=torch.bfloat16, device=dev))
+        return
+    plain = ops.halo_padded_buffer(n, h, w, cout, dev)
+    ops.conv_nhwc(x, wt, bias, ksize=1, cout=cout, relu=True, in_scale=scale, in_shift=shift, out_halo=plain)
+    both = ops.halo_padded_buffer(n, h, w, cout, dev)
+    pooled = torch.full((n, h // 2, w // 2, cin), -7.0, dtype=torch.bfloat16, device=dev)
+    ops.conv_nhwc(x, wt, bias, ksize=1, cout=cout, relu=True, in_scale=scale, in_shift=shift, out_halo=both, pool_in=pooled)
+    torch.cuda.synchronize()
+    ops.check_err_word(dev)
+    assert torch.equal(both, plain)
+    assert torch.equal(pooled, ops.maxpool2x2(x))
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 2, stride=2).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(pooled, ref)
+
 
 # ------------------------------------------------------------------------------------------ bandwidth kernels
 @pytest.mark.parametrize("shape", [(2, 64, 64, 256), (3, 8, 8, 128), (1, 4, 6, 64), (5, 2, 2, 256)])

@@ -184,6 +184,7 @@ def test_pool_fusion_does_not_change_the_network(monkeypatch):
     sd, model = _build(2, 16)
     x = torch.randn(3, 3, 128, 128, generator=torch.Generator().manual_seed(8)).cuda()
     outs = {}
+    monkeypatch.setattr(E, "POOL_IN", False)          # the producer-side fusion alone (the consumer-side one: next test)
     for fuse in (True, False):
         monkeypatch.setattr(E, "FUSE_POOL", fuse)
         eng = E.HourglassEngine(sd, "cuda:0")
@@ -195,5 +196,31 @@ def test_pool_fusion_does_not_change_the_network(monkeypatch):
     # three pools per stack (32^2, 16^2, 8^2 inputs: K3 of a bottleneck, K = 128) ride in their producers' epilogues, plus
     # the first stack's 64^2 input (layer3's K3); the later 64^2 inputs come from the K = 256 remap GEMM and keep the kernel
     assert outs[True][1] == outs[False][1] - (2 * 3 + 1)
+    for a, b in zip(outs[True][0], outs[False][0]):
+        assert torch.equal(a, b)
+
+
+
+def test_pool_from_the_up1_prologue_does_not_change_the_network(monkeypatch):
+    """hg_conv_desc.pool_in (engine.POOL_IN): a level's pooled input comes out of the prologue of the 1x1 conv that opens the
+    level's up1 bottleneck, which is emitted BEFORE the lower pyramid instead of after it.  Same heat maps bit for bit, one
+    launch fewer per level that takes the halo path (here 32^2 and 16^2: 4 rows of 128^2 input, two stacks)."""
+    import hgb200.engine as E
+    sd, model = _build(2, 16)
+    x = torch.randn(4, 3, 128, 128, generator=torch.Generator().manual_seed(9)).cuda()
+    outs = {}
+    monkeypatch.setattr(E, "FUSE_POOL", False)
+    for pool_in in (True, False):
+        monkeypatch.setattr(E, "POOL_IN", pool_in)
+        eng = E.HourglassEngine(sd, "cuda:0")
+        plan = eng.build_plan(4, 128, 128, use_graph=True)
+        plan.input.copy_(x)
+        plan.run()
+        torch.cuda.synchronize()
+        ops_ = [m["op"] for m in plan.meta]
+        outs[pool_in] = ([o.clone() for o in plan.outputs], plan.num_launches, sum(o.endswith("_poolin") for o in ops_),
+                         sum(o.startswith("maxpool") for o in ops_))
+    assert outs[True][2] == 4 and outs[False][2] == 0
+    assert outs[True][1] == outs[False][1] - 4 and outs[True][3] == outs[False][3] - 4
     for a, b in zip(outs[True][0], outs[False][0]):
         assert torch.equal(a, b)
