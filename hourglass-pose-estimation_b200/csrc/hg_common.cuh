@@ -307,6 +307,11 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));     // two IEEE fused multiply-adds
+    return r;
+}
 __device__ __forceinline__ float f2_lo(unsigned long long a) { return __uint_as_float(static_cast<uint32_t>(a)); }
 __device__ __forceinline__ float f2_hi(unsigned long long a) { return __uint_as_float(static_cast<uint32_t>(a >> 32)); }
 

@@ -37,6 +37,9 @@ constexpr int kMaxAStages = 8;
 constexpr int kMaxRing = 6;
 constexpr int kMaxK = 512;
 constexpr int kSmemLimit = 232448;
+#ifndef HG_C1_FFMA2
+#define HG_C1_FFMA2 1
+#endif
 
 struct Params {
     CUtensorMap map_a;      // (c, m) over `in`
@@ -471,6 +474,12 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
                     const uint32_t sh = smem_u32(s_shift + kb * kBlockK + c * 8);
                     const float4 s0 = lds128f(sc), s1 = lds128f(sc + 16);
                     const float4 h0 = lds128f(sh), h1 = lds128f(sh + 16);
+#if HG_C1_FFMA2
+                    const unsigned long long sc01 = f2_pack(s0.x, s0.y), sc23 = f2_pack(s0.z, s0.w), sc45 = f2_pack(s1.x, s1.y),
+                                             sc67 = f2_pack(s1.z, s1.w);
+                    const unsigned long long sh01 = f2_pack(h0.x, h0.y), sh23 = f2_pack(h0.z, h0.w), sh45 = f2_pack(h1.x, h1.y),
+                                             sh67 = f2_pack(h1.z, h1.w);
+#endif
                     const uint32_t a_base = smem_u32(smem_a + stage * kSlabBytes);
                     uint32_t addr[8];
                     uint4 d[8];
@@ -504,10 +513,22 @@ __global__ void __launch_bounds__(kPrologue ? 384 : 256, 1) conv1x1_kernel(const
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         uint4 o;
+#if HG_C1_FFMA2
+                        // packed fp32 pairs (FFMA2): bit-identical to two scalar fmaf, half the arithmetic instructions
+                        const unsigned long long r0 = f2_fma(f2_pack(bf16_lo_to_f32(d[i].x), bf16_hi_to_f32(d[i].x)), sc01, sh01);
+                        const unsigned long long r1 = f2_fma(f2_pack(bf16_lo_to_f32(d[i].y), bf16_hi_to_f32(d[i].y)), sc23, sh23);
+                        const unsigned long long r2 = f2_fma(f2_pack(bf16_lo_to_f32(d[i].z), bf16_hi_to_f32(d[i].z)), sc45, sh45);
+                        const unsigned long long r3 = f2_fma(f2_pack(bf16_lo_to_f32(d[i].w), bf16_hi_to_f32(d[i].w)), sc67, sh67);
+                        o.x = pack_bf16x2_relu(f2_lo(r0), f2_hi(r0));
+                        o.y = pack_bf16x2_relu(f2_lo(r1), f2_hi(r1));
+                        o.z = pack_bf16x2_relu(f2_lo(r2), f2_hi(r2));
+                        o.w = pack_bf16x2_relu(f2_lo(r3), f2_hi(r3));
+#else
                         o.x = pack_bf16x2_relu(fmaf(bf16_lo_to_f32(d[i].x), s0.x, h0.x), fmaf(bf16_hi_to_f32(d[i].x), s0.y, h0.y));
                         o.y = pack_bf16x2_relu(fmaf(bf16_lo_to_f32(d[i].y), s0.z, h0.z), fmaf(bf16_hi_to_f32(d[i].y), s0.w, h0.w));
                         o.z = pack_bf16x2_relu(fmaf(bf16_lo_to_f32(d[i].z), s1.x, h1.x), fmaf(bf16_hi_to_f32(d[i].z), s1.y, h1.y));
                         o.w = pack_bf16x2_relu(fmaf(bf16_lo_to_f32(d[i].w), s1.z, h1.z), fmaf(bf16_hi_to_f32(d[i].w), s1.w, h1.w));
+#endif
                         sts128(addr[i], o);
                     }
                     fence_proxy_async_smem();
