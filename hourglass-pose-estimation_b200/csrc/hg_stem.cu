@@ -5,11 +5,17 @@
 //      ([n][h][w+8][4], 8 bytes per pixel).  Optional left-right mirroring (flip test).
 //   2. hg_stem_conv: implicit GEMM on tcgen05.  For output pixel (oy, ox) and filter row ky, the seven
 //      taps x three channels it needs are the 8-pixel window [2ox-4, 2ox+4) of input row 2oy-3+ky:
-//      32 contiguous bf16.  Consecutive ox are 2 pixels = 16 bytes apart, so ONE 4-D tensor map with
-//      OVERLAPPING strides  (32 elems | ox: 16 B | iy: row pitch | n)  lets a single TMA box load
-//      fetch the [128 pixels x 32] A k-block of a filter row; rows outside the image are zero-filled
-//      by TMA.  K = 7 filter rows x 32 = 224 (weights zero at the unused window slots).
-//      64-byte swizzle (32 bf16 per row); B (28 KiB) stays resident in shared memory.
+//      32 contiguous bf16 = 64 bytes, and consecutive ox are 2 pixels = 16 bytes apart.  So the A operand of a
+//      filter row -- [128 output pixels x 32] -- IS the raw row segment itself (16*128 + 48 bytes), read through an
+//      UMMA descriptor WITHOUT swizzle whose core matrices OVERLAP: in the canonical K-major layout the eight rows
+//      of a core matrix lie 16 bytes apart, the next core matrix along K starts `LBO` bytes later and the next
+//      eight rows `SBO` bytes later; with LBO = 16 and SBO = 128 element (m, k) is read from byte 16 m + 2 k of
+//      the segment, which is exactly window m.  One 2 KB bulk copy per (tile, filter row) replaces a 128-row x
+//      64-byte TMA box (8 KB of shared-memory writes, 4x the L2 reads, and the TMA unit's per-row work -- the
+//      first version of this kernel was bound by exactly that: 353 us against an HBM bound of 112 us, epilogue
+//      warps waiting 46 % of the time, profiles/r2_graph_trace.txt).  Filter rows outside the image are skipped
+//      (zero contribution).  K = 7 filter rows x 32 = 224 (weights zero at the unused window slots); B (28 KiB,
+//      64-byte swizzle) stays resident in shared memory.  Two CTAs per SM: eight epilogue warps.
 #include "hg_common.cuh"
 #include "../../include/hg_api.h"
 
@@ -24,14 +30,16 @@ constexpr int kTileM = 128;
 constexpr int kCout = 64;
 constexpr int kTaps = 7;                         // filter rows = k-blocks
 constexpr int kKb = 32;                          // bf16 per k-block row (8 pixels x 4 channels)
-constexpr int kAStage = kTileM * kKb * 2;        // 8 KiB
+constexpr int kAStage = 2176;                    // one raw row segment: 16 * 128 + 48 = 2096 bytes, rounded up to 128
 constexpr int kBBlock = kCout * kKb * 2;         // 4 KiB
-constexpr int kStages = 8;
+constexpr int kStages = 16;                        // 16 x 2176 B = 34 KiB: keeps the staging slabs behind it 1024-byte aligned
 constexpr int kStaging = kTileM * 128;           // [128 x 64 ch] bf16, 128-byte swizzle
 constexpr int kSmem = 1024 + kTaps * kBBlock + kStages * kAStage + 2 * kStaging + kCout * 4 + 512;
 
 struct Params {
-    CUtensorMap map_a;     // (32, ow, h, n) overlapping windows over the packed image
+    const uint8_t* packed; // [n][h][w+8][4] bf16: the packed image (hg_stem_pack)
+    long long row_pitch;   // bytes per packed image row
+    int h;                 // input rows
     CUtensorMap map_b;     // (224, 64) weights
     CUtensorMap map_out;   // (64, n*oh*ow) output, NHWC bf16
     const float* bias;
@@ -59,7 +67,19 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(256, 1) stem_conv_kernel(const __grid_constant__ Params p) {
+// K-major operand WITHOUT swizzle: 8-row core matrices of 16-byte rows; `lbo` = bytes to the next core matrix along K,
+// `sbo` = bytes to the next 8 rows.
+__device__ __forceinline__ uint64_t umma_desc_noswizzle(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) |
+           (static_cast<uint64_t>(sbo >> 4) << 32) | (static_cast<uint64_t>(1) << 46);
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) stem_conv_kernel(const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_b = smem;                                  // 7 x 4 KiB
@@ -78,7 +98,6 @@ __global__ void __launch_bounds__(256, 1) stem_conv_kernel(const __grid_constant
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < kCout; i += blockDim.x) s_bias[i] = p.bias[i];
     if (warp_idx == 0 && lane == 0) {
-        tma_prefetch_desc(&p.map_a);
         tma_prefetch_desc(&p.map_b);
         tma_prefetch_desc(&p.map_out);
         for (int s = 0; s < kStages; ++s) {
@@ -98,7 +117,7 @@ __global__ void __launch_bounds__(256, 1) stem_conv_kernel(const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // broadcast: provably warp-uniform for the issue loop
     pdl_launch_dependents();
-    const uint32_t a_tx = static_cast<uint32_t>(p.box_w * kKb * 2);
+    const uint32_t a_tx = static_cast<uint32_t>(16 * p.box_w + 48);     // bytes of one raw row segment
 
     if (warp_idx == 0) {
         if (elect_one_sync()) {
@@ -113,10 +132,14 @@ __global__ void __launch_bounds__(256, 1) stem_conv_kernel(const __grid_constant
                 const int row = tile / p.tiles_x;            // n*oh + oy
                 const int n = row / p.oh, oy = row - n * p.oh;
                 for (int ky = 0; ky < kTaps; ++ky) {
+                    const int iy = 2 * oy - 3 + ky;
+                    if (iy < 0 || iy >= p.h) continue;           // a filter row above / below the image contributes nothing
                     ok = mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_word, 0x2101);
                     if (!ok) break;
                     mbar_arrive_expect_tx(&full_bar[stage], a_tx);
-                    tma_load_4d(smem_a + stage * kAStage, &p.map_a, &full_bar[stage], 0, tx * p.box_w, 2 * oy - 3 + ky, n);
+                    bulk_load(smem_a + stage * kAStage,
+                              p.packed + (static_cast<long long>(n) * p.h + iy) * p.row_pitch + static_cast<long long>(tx) * p.box_w * 16,
+                              a_tx, &full_bar[stage]);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
@@ -137,22 +160,27 @@ __global__ void __launch_bounds__(256, 1) stem_conv_kernel(const __grid_constant
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kCout);
+                const int oy = (tile / p.tiles_x) % p.oh;
+                uint32_t have = 0;                               // 0 until the first filter row of this tile has been issued
                 for (int ky = 0; ky < kTaps; ++ky) {
+                    const int iy = 2 * oy - 3 + ky;
+                    if (iy < 0 || iy >= p.h) continue;
                     ok = mbar_wait(&full_bar[stage], phase, p.err_word, 0x2202);
                     if (!ok) break;
                     tc_fence_after();
-                    const uint64_t a_desc = umma_desc_sw64(smem_u32(smem_a + stage * kAStage));
+                    const uint64_t a_desc = umma_desc_noswizzle(smem_u32(smem_a + stage * kAStage), 16, 128);
                     const uint64_t b_desc = umma_desc_sw64(smem_u32(smem_b + ky * kBBlock));
 #pragma unroll
                     for (int k = 0; k < kKb / 16; ++k)
-                        tc_mma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (ky | k) != 0 ? 1u : 0u);
+                        tc_mma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, (have | k) != 0 ? 1u : 0u);
+                    have = 1;
                     tc_commit(&empty_bar[stage]);
-                    if (ky == kTaps - 1) tc_commit(&tmem_full_bar[acc]);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
+                if (ok) tc_commit(&tmem_full_bar[acc]);
             }
         }
     } else if (warp_idx >= 4) {
@@ -268,19 +296,12 @@ extern "C" int hg_stem_conv(const void* packed, const void* weight, const float*
     kp.box_w = kp.ow < kTileM ? kp.ow : kTileM;
     kp.tiles_x = (kp.ow + kp.box_w - 1) / kp.box_w;
     kp.num_tiles = n * kp.oh * kp.tiles_x;
-    const uint64_t pitch = static_cast<uint64_t>(w + 8) * 8;          // bytes per packed image row
-    {
-        cuuint64_t gdim[4] = {kKb, static_cast<cuuint64_t>(kp.ow), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(n)};
-        cuuint64_t gstr[3] = {16, pitch, pitch * h};
-        cuuint32_t box[4] = {kKb, static_cast<cuuint32_t>(kp.box_w), 1, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&kp.map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(packed), gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_last_error("hg_stem_conv: window tensor map failed: CUresult %d", (int)r);
-            return HG_ERR_CUDA;
-        }
+    kp.packed = static_cast<const uint8_t*>(packed);
+    kp.row_pitch = static_cast<long long>(w + 8) * 8;                  // bytes per packed image row
+    kp.h = h;
+    if (reinterpret_cast<uintptr_t>(packed) & 15u) {
+        set_last_error("hg_stem_conv: the packed image must be 16-byte aligned");
+        return HG_ERR_INVALID;
     }
     {
         cuuint64_t gdim[2] = {kTaps * kKb, kCout};
@@ -320,7 +341,7 @@ extern "C" int hg_stem_conv(const void* packed, const void* weight, const float*
             if (dev < 64) done_mask |= 1ull << dev;
         }
     }
-    const int grid = kp.num_tiles < num_sms() ? kp.num_tiles : num_sms();
+    const int grid = kp.num_tiles < 2 * num_sms() ? kp.num_tiles : 2 * num_sms();     // two CTAs per SM
     HG_CUDA_OK(launch_kernel(stem_conv_kernel, dim3(grid), dim3(256), kSmem, static_cast<cudaStream_t>(stream), kp));
     return HG_OK;
 }
