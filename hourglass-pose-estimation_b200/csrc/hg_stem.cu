@@ -58,12 +58,14 @@ __global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict_
         const int x = static_cast<int>(i % w);
         const long long row = i / w;                     // n*h + y
         const long long b = row / h;
-        const long long src = b * 3 * plane + (row - b * h) * w + (flip_w ? (w - 1 - x) : x);
+        const long long src = b * 3 * plane + (row - b * h) * w + (flip_w == 1 ? (w - 1 - x) : x);
         const float r = __ldg(in + src), g = __ldg(in + src + plane), bl = __ldg(in + src + 2 * plane);
         uint2 o;
         o.x = pack_bf16x2(r, g);
         o.y = pack_bf16x2(bl, 0.f);
         out[row * (w + 8) + 4 + x] = o;
+        // flip_w == 2: both orientations from one read -- the mirrored copy goes to the second half of a [2n] buffer
+        if (flip_w == 2) out[(static_cast<long long>(n) * h + row) * (w + 8) + 4 + (w - 1 - x)] = o;
     }
 }
 

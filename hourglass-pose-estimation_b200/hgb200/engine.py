@@ -435,10 +435,9 @@ class HourglassEngine:
         plan.keep = [packed]
         pack_bytes = n * 3 * h * w * 4 + n * h * w * 8
         if both:
-            pk0, pk1 = packed[:n], packed[n:]
-            L.append(lambda a=pk0: ops.stem_pack(x_in, a, flip_w=False))
-            L.append(lambda a=pk1: ops.stem_pack(x_in, a, flip_w=True))
-            plan.meta += [dict(op="stem_pack", kind="bw", flops=0.0, bytes=pack_bytes)] * 2
+            # both orientations of the flip test from ONE read of the fp32 image
+            L.append(lambda a=packed: ops.stem_pack(x_in, a, flip_w="both"))
+            plan.meta.append(dict(op="stem_pack_both", kind="bw", flops=0.0, bytes=pack_bytes + n * h * w * 8))
         else:
             L.append(lambda a=packed: ops.stem_pack(x_in, a, flip_w=bool(flip)))
             plan.meta.append(dict(op="stem_pack", kind="bw", flops=0.0, bytes=pack_bytes))

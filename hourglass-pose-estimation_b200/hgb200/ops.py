@@ -236,12 +236,15 @@ def stem_packed_buffer(n: int, h: int, w: int, device) -> torch.Tensor:
     return torch.zeros((n, h, w + 8, 4), dtype=torch.bfloat16, device=device)
 
 
-def stem_pack(x_nchw: torch.Tensor, packed: torch.Tensor, flip_w: bool = False) -> torch.Tensor:
+def stem_pack(x_nchw: torch.Tensor, packed: torch.Tensor, flip_w=False) -> torch.Tensor:
+    """flip_w: False / True (mirrored), or "both": `packed` is [2n,h,w+8,4], images first, mirrors second, one read."""
     _require_cuda(x_nchw, packed)
     n, c, h, w = x_nchw.shape
-    if c != 3 or x_nchw.dtype != torch.float32 or tuple(packed.shape) != (n, h, w + 8, 4) or packed.dtype != torch.bfloat16:
-        raise HgError("stem_pack: expects fp32 [n,3,h,w] and a bf16 [n,h,w+8,4] buffer")
-    lib.check(lib.hg_stem_pack(_ptr(x_nchw), _ptr(packed), n, h, w, int(flip_w), _stream()), "hg_stem_pack")
+    both = flip_w == "both"
+    if (c != 3 or x_nchw.dtype != torch.float32 or tuple(packed.shape) != ((2 * n if both else n), h, w + 8, 4)
+            or packed.dtype != torch.bfloat16 or not packed.is_contiguous()):
+        raise HgError("stem_pack: expects fp32 [n,3,h,w] and a contiguous bf16 [n (2n for both orientations),h,w+8,4] buffer")
+    lib.check(lib.hg_stem_pack(_ptr(x_nchw), _ptr(packed), n, h, w, 2 if both else int(bool(flip_w)), _stream()), "hg_stem_pack")
     return packed
 
 

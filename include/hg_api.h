@@ -139,7 +139,9 @@ int hg_stem_im2col(const float* in_nchw, void* out_rows, int32_t n, int32_t h, i
 
 /* Stem without an im2col matrix (preferred path):
  *   hg_stem_pack : NCHW fp32 [n][3][h][w] -> NHWC4 bf16 [n][h][w+8][4] (interior only; the caller zero-
- *                  initialises the buffer once so the 4+4 padding pixels stay zero); flip_w mirrors.
+ *                  initialises the buffer once so the 4+4 padding pixels stay zero); flip_w = 1 mirrors; flip_w = 2
+ *                  writes BOTH orientations from one read: `packed` is then [2n][h][w+8][4], images first, their
+ *                  left-right mirrors second (the flip test's batch).
  *   hg_stem_conv : implicit GEMM over 8-pixel windows fetched by an overlapping-stride TMA tensor map.
  *                  weight: bf16 [64][224], k = ky*32 + (1+kx)*4 + c, zero at unused slots; bias fp32 [64];
  *                  out: bf16 NHWC [n][h/2][w/2][64] = relu(conv7x7s2(x) + bias). */

@@ -280,6 +280,13 @@ def test_stem_window_conv(shape, ops, dev):
         ref = F.relu(F.conv2d(r16(xin).to(dev), r16(wt).to(dev), bias.to(dev), stride=2, padding=3))
         err = float((out.float().permute(0, 3, 1, 2) - ref).abs().max())
         assert err <= float(ref.abs().max()) * 2 ** -7, f"err {err}"
+    # both orientations of the flip test from one read: [images | mirrors]
+    a, b, both = (ops.stem_packed_buffer(k, h, w, dev) for k in (n, n, 2 * n))
+    ops.stem_pack(x.to(dev), a, flip_w=False)
+    ops.stem_pack(x.to(dev), b, flip_w=True)
+    ops.stem_pack(x.to(dev), both, flip_w="both")
+    assert torch.equal(both[:n], a) and torch.equal(both[n:], b)
+
 
 @pytest.mark.parametrize("shape", [(2, 64, 64, 256), (3, 32, 32, 256), (8, 16, 16, 256), (2, 64, 64, 128), (5, 32, 32, 256), (1, 8, 8, 256)])
 def test_conv1x1_prologue_also_writes_the_pooled_input(shape, ops, dev):
