@@ -4,12 +4,16 @@
 forward(x: fp32 NCHW [B,3,H,W]) -> python list of num_stacks fp32 tensors [B,num_classes,H/4,W/4],
 exactly what the reference's runners consume (trainer.py:89-91, estimator.py:88).
 """
+from operator import attrgetter
+
 import torch
 import torch.nn as nn
 
 from src.models.modules import Hourglass, HGBottleneck
 
 __all__ = ['HourglassNet', 'hg']
+
+_VERSION = attrgetter('_version')
 
 
 class HourglassNet(nn.Module):
@@ -83,9 +87,20 @@ class HourglassNet(nn.Module):
     # ------------------------------------------------------------------ sm_100a execution
     def _weights_key(self, device):
         # in-place updates (optimizer.step, load_state_dict's copy_) bump tensor._version
-        # (the fused training step updates parameters through raw pointers and bumps _weights_epoch instead)
-        return (str(device), sum(int(t._version) for t in self.state_dict(keep_vars=True).values()),
-                tuple(id(p) for p in self.parameters()), getattr(self, "_weights_epoch", 0))
+        # (the fused training step updates parameters through raw pointers and bumps _weights_epoch instead).
+        # Read straight from the leaf modules' own dictionaries: state_dict() / parameters() rebuild name prefixes and walk
+        # the module tree through generators on every call -- 1.4 ms per forward for the 8-stack network, more than the
+        # batch-1 forward's GPU time (scripts/estimate.py's case).  The module LIST is cached (this network never grows
+        # submodules after construction); the tensors are looked up each time, so a replaced Parameter is still seen.
+        leaves = self.__dict__.get("_key_leaves")
+        if leaves is None:
+            leaves = [(m._parameters, m._buffers) for m in self.modules() if m._parameters or m._buffers]
+            self.__dict__["_key_leaves"] = leaves
+        ps = [t for pd, _ in leaves for t in pd.values() if t is not None]
+        bs = [t for _, bd in leaves for t in bd.values() if t is not None]
+        version = sum(map(_VERSION, ps)) + sum(map(_VERSION, bs))
+        ident = sum(map(id, ps))
+        return (str(device), version, ident, getattr(self, "_weights_epoch", 0))
 
     def engine(self, device=None):
         """The folded-weight inference engine for the current parameters (rebuilt when they change)."""

@@ -53,3 +53,36 @@ def test_product_path_fails_loudly_without_cuda():
         ops.decode_argmax(torch.zeros(1, 1, 4, 4))
     with pytest.raises(HgError):
         ops.normalize_u8(torch.zeros(1, 4, 4, 3, dtype=torch.uint8), [0, 0, 0], [1, 1, 1])
+
+
+def test_weights_key_of_the_model_sees_every_kind_of_update_and_is_cheap():
+    """HourglassNet._weights_key decides whether the folded inference engine is still valid; it runs on EVERY forward, so it
+    must be cheap (it used to cost more than the batch-1 forward itself) and must change on in-place updates, on
+    load_state_dict, on a replaced Parameter and on the fused training step's epoch counter."""
+    import time
+    import torch
+    from src.models import hg
+    model = hg(num_stacks=8, num_blocks=1, num_classes=16, mobile=False, skip_mode="sum")
+    k0 = model._weights_key("cuda:0")
+    assert model._weights_key("cuda:0") == k0 and model._weights_key("cuda:1") != k0
+    with torch.no_grad():
+        model.score[3].bias.add_(1.0)
+    k1 = model._weights_key("cuda:0")
+    assert k1 != k0
+    model.hg[2].hg[0][0][0].bn1.running_mean.mul_(0.5)                       # a buffer
+    k2 = model._weights_key("cuda:0")
+    assert k2 != k1
+    model.load_state_dict({k: v.clone() for k, v in model.state_dict().items()})
+    k3 = model._weights_key("cuda:0")
+    assert k3 != k2
+    model.fc[0][0].weight = torch.nn.Parameter(model.fc[0][0].weight.detach().clone())     # a replaced Parameter object
+    k4 = model._weights_key("cuda:0")
+    assert k4 != k3
+    model._weights_epoch = 5
+    assert model._weights_key("cuda:0") != k4
+    t0 = time.perf_counter()
+    for _ in range(20):
+        model._weights_key("cuda:0")
+    per_call = (time.perf_counter() - t0) / 20
+    assert per_call < 1e-3, per_call
+    print(f"_weights_key: {per_call * 1e6:.0f} us per call")
