@@ -398,6 +398,7 @@ class TrainPlan:
         self.fwd_bytes = 0
         self.bwd_arena_bytes = 0
         self.pending_backward = False       # autograd drop-in: a forward whose backward has not run yet
+        self.generation = 0                 # ... and which forward the static buffers currently belong to
         self.deterministic = False
         self.keep: List[torch.Tensor] = []
         self.scr = lambda t: None
@@ -1112,21 +1113,24 @@ class _TrainFn(torch.autograd.Function):
     def forward(ctx, x, anchor, eng: TrainEngine, use_graph: bool):
         n, _, h, w = x.shape
         plan = eng.plan_for(n, h, w)
-        if plan.pending_backward:
-            # the saved activations live in the plan's static buffers: a second forward of the same shape would
-            # overwrite what the pending backward reads (gradient accumulation over micro-batches of one shape is not
-            # supported on this path; use a larger batch or call backward first)
-            raise HgError("HourglassNet.forward (train mode) re-entered before the backward pass of the previous forward "
-                          "of the same shape has run")
+        # The saved activations live in the plan's static buffers: a second forward of the same shape overwrites what the
+        # backward of the first would read.  A forward whose backward never runs (logging, evaluation in train mode) is
+        # legitimate, so re-entry is allowed and every forward takes a new generation number; backward() refuses to run on
+        # a forward that is no longer the plan's latest (gradient accumulation over micro-batches of ONE shape is not
+        # supported on this path: use a larger batch, or call backward before the next forward).
+        plan.generation += 1
         plan.input.copy_(x, non_blocking=True)
         plan.run("fwd", use_graph)
         plan.pending_backward = True
-        ctx.plan, ctx.eng, ctx.use_graph = plan, eng, use_graph
+        ctx.plan, ctx.eng, ctx.use_graph, ctx.generation = plan, eng, use_graph, plan.generation
         return tuple(o.clone() for o in plan.outputs)
 
     @staticmethod
     def backward(ctx, *grads):
         plan, eng = ctx.plan, ctx.eng
+        if ctx.generation != plan.generation:
+            raise HgError("HourglassNet backward: another forward of the same shape has run since this one; its saved "
+                          "activations (the plan's static buffers) are gone")
         for dst, g in zip(plan.dheat, grads):
             if g is None:
                 dst.zero_()

@@ -108,8 +108,9 @@ def maxpool2x2(x, out=None):
 
 
 def maxpool2x2_bwd(x, dpool, dx, accumulate):
-    xf = _nchw(x).requires_grad_(True)
-    F.max_pool2d(xf, 2, 2).backward(_nchw(dpool))
+    with torch.enable_grad():          # the plan may be running inside an autograd.Function (grad mode off there)
+        xf = _nchw(x).detach().requires_grad_(True)
+        F.max_pool2d(xf, 2, 2).backward(_nchw(dpool))
     g = xf.grad
     if accumulate:
         g = g + _nchw(dx)

@@ -145,3 +145,42 @@ def test_cpu_model_training_fails_loudly():
     model = hg(num_stacks=1, num_blocks=1, num_classes=16, mobile=False, skip_mode="sum").train()
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 3, 64, 64))
+
+
+def test_autograd_dropin_forward_may_be_repeated_but_a_stale_backward_is_refused(cpu_train, monkeypatch):
+    """model(x) in train mode under the reference's own loop (trainer.py:89-99).  The saved activations are the plan's static
+    buffers: a forward whose backward never runs is fine (logging / evaluation in train mode), the backward of a forward
+    that is no longer the latest of its shape must fail loudly instead of using another batch's activations."""
+    from hgb200 import HgError
+    from src.models import hg
+    monkeypatch.setattr(cpu_train, "_ACT", torch.float32)
+    monkeypatch.setattr(fake_ops, "BF", torch.float32)
+    S, J, B, H, W = 1, 16, 3, 128, 128      # (at 64x64 the lowest level is 1x1: batch statistics over B values are degenerate)
+    model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum")
+    model.load_state_dict(make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, seed=0))
+    model.train()
+    model.use_cuda_graph = False
+    (x, tg, tw), (x2, _, _) = train_inputs(1, B, J, H, W, 2)
+
+    def crit(outs, target, weight):
+        """src/loss/mse.py:14-44 in plain torch ops (the product's MSELoss is a CUDA kernel)."""
+        total = 0.0
+        for o in outs:
+            b, j = o.shape[:2]
+            p, g = o.reshape(b, j, -1), target.reshape(b, j, -1)
+            per = sum(0.5 * torch.mean((p[:, k] * weight[:, k] - g[:, k] * weight[:, k]) ** 2) for k in range(j))
+            total = total + per / j
+        return total
+
+    out_a = model(x)                     # never back-propagated
+    out_b = model(x2)
+    out_c = model(x)                     # the latest forward of this shape
+    assert all(torch.equal(a, c) for a, c in zip(out_a, out_c)) and not torch.equal(out_b[-1], out_c[-1])
+    ref_loss, _, ref_grads = T.forward_backward({k: v.detach().clone() for k, v in model.state_dict().items()}, x, tg, tw)
+    loss = crit(out_c, tg, tw)
+    loss.backward()
+    assert abs(float(loss) - ref_loss) <= 1e-4 * ref_loss
+    g = model.score[0].weight.grad
+    assert float((g - ref_grads["score.0.weight"]).norm()) <= 1e-3 * float(ref_grads["score.0.weight"].norm())
+    with pytest.raises(HgError):
+        crit(out_b, tg, tw).backward()   # out_b's activations were overwritten by the forward that produced out_c
