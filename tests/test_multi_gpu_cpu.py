@@ -96,7 +96,7 @@ def test_data_parallel_step_world2_gloo():
     assert ret["worst"] < 5e-2, ret["worst"]
 
 
-def _ragged_worker(rank, world, port, ret):
+def _ragged_worker(rank, world, port, ret, overlap=False):
     """A ragged last batch (5 images over 2 ranks: shards of 3 and 2, gradient scale = shard / global) and a batch smaller
     than the world (1 image: rank 1 has nothing to compute and joins the all-reduce through idle_step)."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -112,6 +112,12 @@ def _ragged_worker(rank, world, port, ret):
         from src.models import hg
         tr.ops, tr._ACT = fake_ops, torch.float32
         fake_ops.BF = torch.float32
+        tr.OVERLAP_ALLREDUCE = overlap      # bucketed exchange: the eager bucket loop here (the graph needs CUDA)
+        calls = []
+
+        def all_reduce_counted(flat):
+            calls.append(flat.numel())
+            all_reduce_sum(flat)
         S, J, H, W, lr = 1, 16, 128, 128, 2.5e-4
         sd = make_state_dict(num_stacks=S, num_blocks=1, num_classes=J, seed=0)
         model = hg(num_stacks=S, num_blocks=1, num_classes=J, mobile=False, skip_mode="sum")
@@ -125,10 +131,10 @@ def _ragged_worker(rank, world, port, ret):
             before = {k: v.detach().clone() for k, v in model.state_dict().items()}
             a, b = batch_shard(B, world, rank)
             if b > a:
-                eng.train_step(x[a:b], tg[a:b], tw[a:b], lr, use_graph=False, world_size=world, all_reduce=all_reduce_sum,
+                eng.train_step(x[a:b], tg[a:b], tw[a:b], lr, use_graph=False, world_size=world, all_reduce=all_reduce_counted,
                                grad_scale=(b - a) / B)
             else:
-                eng.idle_step(lr, all_reduce_sum)
+                eng.idle_step(lr, all_reduce_counted)
             total = None
             for r in range(world):
                 ra, rb = batch_shard(B, world, r)
@@ -150,16 +156,25 @@ def _ragged_worker(rank, world, port, ret):
         if rank == 0:
             ret["worst"], ret["same"] = worst, all(torch.equal(gathered[0], t) for t in gathered)
             ret["median"] = {b: float(np.median(v)) for b, v in per_b.items()}
+        ret[f"calls{rank}"] = list(calls)
     finally:
         dist.destroy_process_group()
 
 
-def test_ragged_and_idle_shards_world2_gloo():
+@pytest.mark.parametrize("overlap", [False, True])
+def test_ragged_and_idle_shards_world2_gloo(overlap):
+    """overlap=True: the bucketed exchange (HG_OVERLAP_AR=1).  Both ranks must issue the SAME sequence of collectives -- one
+    communicator warm-up, then the same bucket sizes in the same order -- whether a rank runs train_step or idle_step."""
     world = 2
-    port = 31500 + (os.getpid() % 2000)
+    port = 31500 + (os.getpid() % 2000) + (1000 if overlap else 0)
     ret = mp.Manager().dict()
-    mp.spawn(_ragged_worker, args=(world, port, ret), nprocs=world, join=True)
+    mp.spawn(_ragged_worker, args=(world, port, ret, overlap), nprocs=world, join=True)
     assert ret["same"], "ranks diverged after a ragged / idle step"
+    assert ret["calls0"] == ret["calls1"], (ret["calls0"], ret["calls1"])
+    if overlap:
+        assert ret["calls0"][0] == 4 and len(ret["calls0"]) == 1 + 2 * 3      # warm-up + (hg.0, tail block, stem block) x 2 steps
+    else:
+        assert len(ret["calls0"]) == 2                                         # one whole-buffer all-reduce per step
     # shards of 1-3 images leave 4-12 samples per channel to the train-mode BatchNorms of the 2x2 level, which amplify
     # accumulation-order noise in a handful of tensors; a wrong shard weighting would be off by >= 10 % in EVERY tensor
     assert all(m < 5e-2 for m in ret["median"].values()), dict(ret["median"])
