@@ -287,6 +287,12 @@ extern "C" int hg_stem_conv(const void* packed, const void* weight, const float*
         set_last_error("hg_stem_conv: bad arguments (need even h, w)");
         return HG_ERR_INVALID;
     }
+    if (w / 2 > kTileM && (w / 2) % kTileM != 0) {
+        // a partial last tile per output row would read past the packed row and store past the output row (the output map
+        // is the flat [pixels x 64] matrix): widths above 256 must be multiples of 256
+        set_last_error("hg_stem_conv: input widths above 256 must be multiples of 256 (got %d)", w);
+        return HG_ERR_INVALID;
+    }
     auto enc = encode_fn();
     if (!enc) return HG_ERR_CUDA;
     Params kp;

@@ -144,7 +144,7 @@ int hg_stem_im2col(const float* in_nchw, void* out_rows, int32_t n, int32_t h, i
  *                  left-right mirrors second (the flip test's batch).
  *   hg_stem_conv : implicit GEMM over 8-pixel windows fetched by an overlapping-stride TMA tensor map.
  *                  weight: bf16 [64][224], k = ky*32 + (1+kx)*4 + c, zero at unused slots; bias fp32 [64];
- *                  out: bf16 NHWC [n][h/2][w/2][64] = relu(conv7x7s2(x) + bias). */
+ *                  out: bf16 NHWC [n][h/2][w/2][64] = relu(conv7x7s2(x) + bias).  h, w even; w <= 256 or a multiple of 256. */
 int hg_stem_pack(const float* in_nchw, void* packed, int32_t n, int32_t h, int32_t w, int32_t flip_w, void* stream);
 int hg_stem_conv(const void* packed, const void* weight, const float* bias, void* out, unsigned int* err_word, int32_t n,
                  int32_t h, int32_t w, void* stream);

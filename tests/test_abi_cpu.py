@@ -41,6 +41,11 @@ def test_argument_validation_needs_no_device():
         lib.check(lib.hg_wgrad_bf16(None, None, None, None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, None), "hg_wgrad_bf16")
     assert lib.hg_colstats_nhwc(None, None, None, 0, 64, 64, 0, None, None) != 0
     assert lib.hg_colreduce_scratch_bytes(0, 64) == 0 and lib.hg_colreduce_scratch_bytes(64, 48) == 0
+    # the windowed stem: tiles are runs of 128 output pixels of ONE output row; a width whose rows do not split into whole
+    # tiles is refused (it would read past the packed row and store past the output row), before any CUDA call
+    dummy = C.c_void_p(16)
+    assert lib.hg_stem_conv(dummy, dummy, dummy, dummy, None, 1, 64, 384, None) != 0
+    assert lib.hg_last_error(buf, 256) > 0 and b"multiples of 256" in buf.value
 
 
 def test_product_path_fails_loudly_without_cuda():
